@@ -1,0 +1,56 @@
+"""ctypes binding of include/musev_b200.h. There is no fallback: if the library is missing, loading raises."""
+from __future__ import annotations
+
+import ctypes as C
+import os
+
+from .build import LIB_PATH
+
+_lib = None
+
+
+class MvbError(RuntimeError):
+    pass
+
+
+class ConvGemmDesc(C.Structure):
+    _fields_ = [
+        ("a0", C.c_void_p), ("c0", C.c_int),
+        ("a0_stride_w", C.c_longlong), ("a0_stride_h", C.c_longlong), ("a0_stride_n", C.c_longlong),
+        ("a1", C.c_void_p), ("c1", C.c_int),
+        ("a1_stride_w", C.c_longlong), ("a1_stride_h", C.c_longlong), ("a1_stride_n", C.c_longlong),
+        ("W", C.c_int), ("H", C.c_int), ("NF", C.c_int),
+        ("ntaps", C.c_int), ("dy", C.c_int8 * 9), ("dx", C.c_int8 * 9),
+        ("weight", C.c_void_p), ("N", C.c_int),
+        ("out", C.c_void_p), ("ldc", C.c_longlong),
+        ("bias", C.c_void_p),
+        ("rowadd", C.c_void_p), ("rows_per_group", C.c_int), ("ld_rowadd", C.c_int),
+        ("residual", C.c_void_p), ("ld_res", C.c_longlong),
+        ("alpha", C.c_float), ("beta", C.c_float),
+        ("geglu", C.c_int), ("act", C.c_int),
+    ]
+
+
+def lib() -> C.CDLL:
+    """Load libmusevb200.so (built in-tree by musev_b200.build). Raises if it is not there."""
+    global _lib
+    if _lib is None:
+        if not os.path.exists(LIB_PATH):
+            raise MvbError(
+                f"{LIB_PATH} not found: build it with `python -m musev_b200.build` "
+                "(musev_b200 has no CPU or PyTorch fallback)")
+        _lib = C.CDLL(LIB_PATH)
+        _lib.mvb_last_error.restype = C.c_char_p
+        _declare(_lib)
+    return _lib
+
+
+def _declare(l: C.CDLL) -> None:
+    l.mvb_version.restype = C.c_int
+    l.mvb_op_conv_gemm.argtypes = [C.POINTER(ConvGemmDesc), C.c_void_p]
+    l.mvb_op_conv_gemm.restype = C.c_int
+
+
+def check(rc: int) -> None:
+    if rc != 0:
+        raise MvbError(f"musev_b200 error {rc}: {lib().mvb_last_error().decode()}")

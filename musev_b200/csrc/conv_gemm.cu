@@ -1,0 +1,367 @@
+// tcgen05 / TMA implicit-GEMM kernel. See conv_gemm.cuh for the math and the reference call sites.
+//
+// CTA = 256 threads, persistent over output tiles (128 rows x block_n columns):
+//   warp 0   : TMA producer  -- per K block (64 channels of one tap) loads the A box {64, bw, bh, bn}
+//              (out-of-image taps are zero-filled by TMA = conv padding) and the weight tile {64, block_n}
+//   warp 1   : MMA issuer    -- one thread issues 4 x tcgen05.mma (K=16 each) per K block into TMEM
+//   warp 2   : TMEM allocator (512 columns = 2 accumulator stages x up to 256 fp32 columns)
+//   warps 4-7: epilogue      -- tcgen05.ld accumulator rows, bias / time-embedding / residual / GEGLU, fp16 store
+// Pipelines: smem ring (full/empty mbarriers, 4 stages) and TMEM double buffer (tmem_full/tmem_empty).
+#include "conv_gemm.cuh"
+
+#include <dlfcn.h>
+#include <stdio.h>
+
+#include "ptx.cuh"
+
+namespace mvb {
+
+static constexpr int kStages = 4;
+static constexpr int kBlockM = 128;
+static constexpr int kBlockK = 64;
+static constexpr int kMaxBlockN = 256;
+static constexpr int kABytes = kBlockM * kBlockK * 2;        // 16 KB
+static constexpr int kBBytes = kMaxBlockN * kBlockK * 2;     // 32 KB
+static constexpr int kStageBytes = kABytes + kBBytes;
+static constexpr int kSmemBytes = kStages * kStageBytes + 1024 /*align*/ + 256 /*barriers*/;
+
+__device__ __forceinline__ float gelu_erf(float x) { return 0.5f * x * (1.f + erff(x * 0.70710678118654752440f)); }
+__device__ __forceinline__ float silu(float x) { return x / (1.f + __expf(-x)); }
+
+__global__ void __launch_bounds__(256, 1)
+conv_gemm_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__ CUtensorMap tmA1,
+                 const __grid_constant__ CUtensorMap tmB, const __grid_constant__ ConvGemmParams p) {
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + kStages * kStageBytes);
+  uint64_t* full = bars;                    // [kStages]
+  uint64_t* empty = bars + kStages;         // [kStages]
+  uint64_t* tfull = bars + 2 * kStages;     // [2]
+  uint64_t* tempty = bars + 2 * kStages + 2;// [2]
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * kStages + 4);
+
+  const int warp = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
+
+  if (warp == 0 && lane == 0) {
+    tma_prefetch_desc(&tmA0);
+    tma_prefetch_desc(&tmA1);
+    tma_prefetch_desc(&tmB);
+  }
+  if (warp == 1 && lane == 0) {
+    for (int s = 0; s < kStages; ++s) {
+      mbar_init(&full[s], 1);
+      mbar_init(&empty[s], 1);
+    }
+    for (int s = 0; s < 2; ++s) {
+      mbar_init(&tfull[s], 1);
+      mbar_init(&tempty[s], 4);
+    }
+    fence_barrier_init();
+  }
+  if (warp == 2) {
+    tmem_alloc(tmem_slot, 512);
+    tmem_relinquish();
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  const int kb_per_tap = p.kb0 + p.kb1;
+  const int num_kb = p.ntaps * kb_per_tap;
+  const int tiles_m = p.tiles_w * p.tiles_h * p.tiles_n;
+  const int num_tiles = tiles_m * p.tiles_nn;
+  const uint32_t stage_tx = kABytes + (uint32_t)p.block_n * kBlockK * 2;
+
+  if (warp == 0) {
+    if (lane == 0) {
+      int stage = 0;
+      uint32_t phase = 0;
+      for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+        const int nt = tile % p.tiles_nn;
+        const int mt = tile / p.tiles_nn;
+        const int tw = mt % p.tiles_w;
+        const int th = (mt / p.tiles_w) % p.tiles_h;
+        const int tn = mt / (p.tiles_w * p.tiles_h);
+        const int w0 = tw * p.bw, h0 = th * p.bh, n0 = tn * p.bn;
+        for (int kb = 0; kb < num_kb; ++kb) {
+          const int tap = kb / kb_per_tap;
+          const int cb = kb - tap * kb_per_tap;
+          mbar_wait(&empty[stage], phase ^ 1);
+          uint8_t* sa = smem + stage * kStageBytes;
+          uint8_t* sb = sa + kABytes;
+          mbar_expect_tx(&full[stage], stage_tx);
+          if (cb < p.kb0)
+            tma_load_4d(sa, &tmA0, &full[stage], cb * kBlockK, w0 + p.dx[tap], h0 + p.dy[tap], n0);
+          else
+            tma_load_4d(sa, &tmA1, &full[stage], (cb - p.kb0) * kBlockK, w0 + p.dx[tap], h0 + p.dy[tap], n0);
+          tma_load_2d(sb, &tmB, &full[stage], kb * kBlockK, nt * p.block_n);
+          if (++stage == kStages) { stage = 0; phase ^= 1; }
+        }
+      }
+    }
+  } else if (warp == 1) {
+    if (lane == 0) {
+      const uint32_t idesc = make_idesc_f16(kBlockM, p.block_n, 0, 0);
+      int stage = 0;
+      uint32_t phase = 0;
+      int as = 0;
+      uint32_t aphase = 0;
+      for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+        mbar_wait(&tempty[as], aphase ^ 1);
+        tc_fence_after();
+        const uint32_t d_tmem = tmem_base + (uint32_t)as * kMaxBlockN;
+        for (int kb = 0; kb < num_kb; ++kb) {
+          mbar_wait(&full[stage], phase);
+          tc_fence_after();
+          const uint32_t sa = smem_u32(smem + stage * kStageBytes);
+          const uint32_t sb = sa + kABytes;
+          const uint64_t da = make_desc_k_sw128(sa);
+          const uint64_t db = make_desc_k_sw128(sb);
+#pragma unroll
+          for (int k = 0; k < kBlockK / 16; ++k) {
+            // advance 16 K-elements = 32 bytes inside the 128-byte swizzle atom: +2 in the (addr >> 4) field
+            umma_f16_ss(d_tmem, da + (uint64_t)(k * 2), db + (uint64_t)(k * 2), idesc, (kb | k) != 0);
+          }
+          umma_commit(&empty[stage]);
+          if (++stage == kStages) { stage = 0; phase ^= 1; }
+        }
+        umma_commit(&tfull[as]);
+        if (++as == 2) { as = 0; aphase ^= 1; }
+      }
+    }
+  } else if (warp >= 4) {
+    const int q = warp & 3;          // TMEM lane quarter this warp may read
+    const int r = q * 32 + lane;     // accumulator row
+    int as = 0;
+    uint32_t aphase = 0;
+    const int nout = p.geglu ? p.N / 2 : p.N;
+    for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+      const int nt = tile % p.tiles_nn;
+      const int mt = tile / p.tiles_nn;
+      const int tw = mt % p.tiles_w;
+      const int th = (mt / p.tiles_w) % p.tiles_h;
+      const int tn = mt / (p.tiles_w * p.tiles_h);
+      const int rw = r % p.bw;
+      const int rh = (r / p.bw) % p.bh;
+      const int rn = r / (p.bw * p.bh);
+      const int w = tw * p.bw + rw, h = th * p.bh + rh, n = tn * p.bn + rn;
+      const bool row_ok = (w < p.W) && (h < p.H) && (n < p.NF);
+      const long long m = ((long long)n * p.H + h) * p.W + w;
+      const float* radd = p.rowadd ? p.rowadd + (long long)(m / p.rows_per_group) * p.ld_rowadd : nullptr;
+
+      mbar_wait(&tfull[as], aphase);
+      tc_fence_after();
+      const uint32_t t_row = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)as * kMaxBlockN;
+      const int ncol0 = nt * p.block_n;
+      for (int c0 = 0; c0 < p.block_n; c0 += 32) {
+        uint32_t v[32];
+        const bool full32 = (c0 + 32 <= p.block_n);
+        if (full32) {
+          tmem_ld32(t_row + c0, v);
+        } else {
+          uint32_t v16[16];
+          tmem_ld16(t_row + c0, v16);
+#pragma unroll
+          for (int j = 0; j < 16; ++j) { v[j] = v16[j]; v[16 + j] = 0; }
+        }
+        tmem_ld_wait();
+        if (!row_ok) continue;
+        const int ncols = full32 ? 32 : 16;
+        float f[32];
+#pragma unroll
+        for (int j = 0; j < 32; ++j) {
+          const int nn = ncol0 + c0 + j;
+          float x = __uint_as_float(v[j]);
+          if (j < ncols && nn < p.N) {
+            if (p.bias) x += __ldg(p.bias + nn);
+            if (radd) x += __ldg(radd + nn);
+          }
+          f[j] = x;
+        }
+        if (p.geglu) {
+          // packed chunk: columns [0,16) = value, [16,32) = gate of 16 consecutive output columns
+          const int oc = (ncol0 + c0) / 2;
+          if (oc < nout) {
+            __align__(16) __half o[16];
+#pragma unroll
+            for (int j = 0; j < 16; ++j) o[j] = __float2half_rn(f[j] * gelu_erf(f[16 + j]));
+            uint4* dst = reinterpret_cast<uint4*>(p.out + m * p.ldc + oc);
+            dst[0] = reinterpret_cast<const uint4*>(o)[0];
+            dst[1] = reinterpret_cast<const uint4*>(o)[1];
+          }
+        } else {
+#pragma unroll
+          for (int g = 0; g < 4; ++g) {
+            const int nn = ncol0 + c0 + g * 8;
+            if (g * 8 < ncols && nn < p.N) {
+              __align__(16) __half o[8];
+              float rr[8];
+              if (p.res) {
+                const uint4 rv = __ldg(reinterpret_cast<const uint4*>(p.res + m * p.ld_res + nn));
+                const __half* rh8 = reinterpret_cast<const __half*>(&rv);
+#pragma unroll
+                for (int j = 0; j < 8; ++j) rr[j] = __half2float(rh8[j]);
+              }
+#pragma unroll
+              for (int j = 0; j < 8; ++j) {
+                float x = f[g * 8 + j] * p.alpha;
+                if (p.res) x += p.beta * rr[j];
+                if (p.act == 1) x = silu(x);
+                o[j] = __float2half_rn(x);
+              }
+              *reinterpret_cast<uint4*>(p.out + m * p.ldc + nn) = *reinterpret_cast<const uint4*>(o);
+            }
+          }
+        }
+      }
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&tempty[as]);
+      if (++as == 2) { as = 0; aphase ^= 1; }
+    }
+  }
+
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 2) tmem_dealloc(tmem_base, 512);
+}
+
+// ------------------------------------------------------------------ host side
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
+                                  const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
+                                  CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+EncodeTiledFn get_encode_fn() {
+  static EncodeTiledFn fn = nullptr;
+  static bool tried = false;
+  if (!tried) {
+    tried = true;
+    void* h = dlopen("libcuda.so.1", RTLD_NOW | RTLD_GLOBAL);
+    if (!h) h = dlopen("libcuda.so", RTLD_NOW | RTLD_GLOBAL);
+    if (h) fn = reinterpret_cast<EncodeTiledFn>(dlsym(h, "cuTensorMapEncodeTiled"));
+  }
+  return fn;
+}
+
+// rank-4 fp16 map, inner box 64 elements, 128-byte swizzle, zero fill out of bounds
+bool encode_map_4d(CUtensorMap* m, const void* ptr, const uint64_t dims[4], const uint64_t strides_elems[3],
+                   const uint32_t box[4]) {
+  EncodeTiledFn fn = get_encode_fn();
+  if (!fn) return false;
+  cuuint64_t gd[4] = {dims[0], dims[1], dims[2], dims[3]};
+  cuuint64_t gs[3] = {strides_elems[0] * 2, strides_elems[1] * 2, strides_elems[2] * 2};
+  cuuint32_t bx[4] = {box[0], box[1], box[2], box[3]};
+  cuuint32_t es[4] = {1, 1, 1, 1};
+  CUresult r = fn(m, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 4, const_cast<void*>(ptr), gd, gs, bx, es,
+                  CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                  CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  return r == CUDA_SUCCESS;
+}
+
+bool encode_map_2d(CUtensorMap* m, const void* ptr, uint64_t d0, uint64_t d1, uint64_t stride1_elems, uint32_t b0,
+                   uint32_t b1) {
+  EncodeTiledFn fn = get_encode_fn();
+  if (!fn) return false;
+  cuuint64_t gd[2] = {d0, d1};
+  cuuint64_t gs[1] = {stride1_elems * 2};
+  cuuint32_t bx[2] = {b0, b1};
+  cuuint32_t es[2] = {1, 1};
+  CUresult r = fn(m, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 2, const_cast<void*>(ptr), gd, gs, bx, es,
+                  CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                  CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  return r == CUDA_SUCCESS;
+}
+
+static int ceil_div(int a, int b) { return (a + b - 1) / b; }
+
+// Pick the 128-row pixel box {bw, bh, bn} (powers of two) that wastes the fewest padded rows.
+static void pick_box(int W, int H, int NF, int* bw, int* bh, int* bn) {
+  long long best = -1;
+  for (int w = 128; w >= 1; w >>= 1) {
+    for (int h = 128 / w; h >= 1; h >>= 1) {
+      const int n = 128 / (w * h);
+      const long long padded = (long long)ceil_div(W, w) * ceil_div(H, h) * ceil_div(NF, n);
+      if (best < 0 || padded < best) {
+        best = padded;
+        *bw = w; *bh = h; *bn = n;
+      }
+    }
+  }
+}
+
+static int pick_block_n(int N, int geglu, long long tiles_m, int num_sms) {
+  // candidates are multiples of 32 (GEGLU chunks) or 16; prefer few padded columns, then fewer waves
+  int best = 0;
+  double best_cost = 1e30;
+  for (int bn = 256; bn >= 16; bn -= 16) {
+    if (geglu && (bn % 32)) continue;
+    const int tn = ceil_div(N, bn);
+    const long long tiles = tiles_m * tn;
+    const long long waves = (tiles + num_sms - 1) / num_sms;
+    // time ~ waves * (bn + epilogue/fixed overhead per tile)
+    const double cost = (double)waves * (bn + 24.0);
+    if (cost < best_cost - 1e-9) { best_cost = cost; best = bn; }
+  }
+  return best;
+}
+
+cudaError_t launch_conv_gemm(cudaStream_t stream, const ASource& a0, const ASource* a1, int W, int H, int NF,
+                             int ntaps, const int8_t* dy, const int8_t* dx, const __half* wt, int N,
+                             const Epilogue& ep, int num_sms, const char** err) {
+  static bool attr_set = false;
+  if (!attr_set) {
+    cudaError_t e = cudaFuncSetAttribute(conv_gemm_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemBytes);
+    if (e != cudaSuccess) { *err = "cudaFuncSetAttribute(conv_gemm_kernel)"; return e; }
+    attr_set = true;
+  }
+  if ((a0.C % 64) || (a1 && (a1->C % 64)) || (N % 8) || ntaps < 1 || ntaps > 9) {
+    *err = "conv_gemm: channels must be multiples of 64, N a multiple of 8, 1..9 taps";
+    return cudaErrorInvalidValue;
+  }
+  ConvGemmParams p{};
+  p.W = W; p.H = H; p.NF = NF;
+  pick_box(W, H, NF, &p.bw, &p.bh, &p.bn);
+  p.tiles_w = ceil_div(W, p.bw); p.tiles_h = ceil_div(H, p.bh); p.tiles_n = ceil_div(NF, p.bn);
+  p.ntaps = ntaps;
+  for (int i = 0; i < ntaps; ++i) { p.dy[i] = dy[i]; p.dx[i] = dx[i]; }
+  p.kb0 = a0.C / 64;
+  p.kb1 = a1 ? a1->C / 64 : 0;
+  p.N = N;
+  const long long tiles_m = (long long)p.tiles_w * p.tiles_h * p.tiles_n;
+  p.block_n = pick_block_n(N, ep.geglu, tiles_m, num_sms);
+  p.tiles_nn = ceil_div(N, p.block_n);
+  p.out = ep.out; p.ldc = ep.ldc; p.bias = ep.bias; p.rowadd = ep.rowadd;
+  p.rows_per_group = ep.rows_per_group > 0 ? ep.rows_per_group : 1;
+  p.ld_rowadd = ep.ld_rowadd; p.res = ep.res; p.ld_res = ep.ld_res; p.alpha = ep.alpha; p.beta = ep.beta;
+  p.geglu = ep.geglu; p.act = ep.act;
+
+  CUtensorMap tmA0, tmA1, tmB;
+  const uint32_t box[4] = {64u, (uint32_t)p.bw, (uint32_t)p.bh, (uint32_t)p.bn};
+  {
+    const uint64_t dims[4] = {(uint64_t)a0.C, (uint64_t)W, (uint64_t)H, (uint64_t)NF};
+    const uint64_t st[3] = {(uint64_t)a0.sW, (uint64_t)a0.sH, (uint64_t)a0.sN};
+    if (!encode_map_4d(&tmA0, a0.ptr, dims, st, box)) { *err = "cuTensorMapEncodeTiled(A0) failed"; return cudaErrorInvalidValue; }
+  }
+  if (a1) {
+    const uint64_t dims[4] = {(uint64_t)a1->C, (uint64_t)W, (uint64_t)H, (uint64_t)NF};
+    const uint64_t st[3] = {(uint64_t)a1->sW, (uint64_t)a1->sH, (uint64_t)a1->sN};
+    if (!encode_map_4d(&tmA1, a1->ptr, dims, st, box)) { *err = "cuTensorMapEncodeTiled(A1) failed"; return cudaErrorInvalidValue; }
+  } else {
+    tmA1 = tmA0;
+  }
+  const long long ktot = (long long)ntaps * (a0.C + (a1 ? a1->C : 0));
+  if (!encode_map_2d(&tmB, wt, (uint64_t)ktot, (uint64_t)N, (uint64_t)ktot, 64u, (uint32_t)p.block_n)) {
+    *err = "cuTensorMapEncodeTiled(B) failed";
+    return cudaErrorInvalidValue;
+  }
+  const long long num_tiles = tiles_m * p.tiles_nn;
+  const int grid = (int)(num_tiles < num_sms ? num_tiles : num_sms);
+  conv_gemm_kernel<<<grid, 256, kSmemBytes, stream>>>(tmA0, tmA1, tmB, p);
+  cudaError_t e = cudaGetLastError();
+  if (e != cudaSuccess) *err = "conv_gemm_kernel launch";
+  return e;
+}
+
+}  // namespace mvb
