@@ -55,9 +55,133 @@ typedef struct mvb_conv_gemm_desc {
   float alpha, beta;
   int geglu;
   int act; /* 0 none, 1 SiLU */
+  int out_f32; /* store fp32 (no residual / geglu) */
+  int stride2; /* 1: 3x3 stride-2 pad-1 conv of a contiguous [NF,H,W,c0] input (taps ignored) */
 } mvb_conv_gemm_desc;
 
 int mvb_op_conv_gemm(const mvb_conv_gemm_desc* desc, void* stream);
+
+
+/* ---------------------------------------------------------------------------------------------------------
+ * Op level: flash attention on tcgen05 (spatial self / reference / cross attention of the transformer blocks).
+ *
+ * Replaces xformers.ops.memory_efficient_attention at musev/models/attention_processor.py:258,292,519,724 and
+ * F.scaled_dot_product_attention at diffusers/src/diffusers/models/attention_processor.py:1166-1250.
+ * Q/K/V are head-padded token matrices (head h occupies columns [h*dp, h*dp+d), dp a multiple of 16, padding = 0);
+ * the keys of query frame f are the concatenation of up to two segments, segment s starting at row
+ * (f / fdiv[s]) * fmul[s] + fadd[s] of its K/V matrices and holding nk[s] rows.
+ *   out[f*Nq + q, h*d + :] (+)= out_scale * softmax_k(scale * q.k) v
+ */
+typedef struct mvb_attention_desc {
+  const void* q; long long ldq;
+  int NF, Nq, heads, d, dp;
+  float scale;
+  int nseg;
+  const void* k[2]; const void* v[2]; long long ldkv[2]; long long kv_rows[2];
+  int nk[2]; int fdiv[2]; long long fmul[2]; long long fadd[2];
+  void* out; long long ldo;
+  float out_scale;
+  int accumulate;
+} mvb_attention_desc;
+
+int mvb_op_attention(const mvb_attention_desc* desc, void* stream);
+
+/* Temporal self-attention over the frame axis (musev/models/temporal_transformer.py:241-273 ->
+ * musev/models/attention.py:293-365 -> AttnProcessor2_0). qkv: [B, T, HW, 3*heads*dp] (q | k | v). */
+int mvb_op_temporal_attention(const void* qkv, int ld, int B, int T, int HW, int heads, int d, int dp, float scale,
+                              void* out, int ldo, void* stream);
+
+/* GroupNorm (+SiLU) on channels-last fp16 [NF, HW, C0 (+C1)] (F.group_norm at diffusers models/resnet.py:641,662;
+ * musev/models/resnet.py:57-74; temporal_transformer.py:117). frames_per_stat = 1: per-frame statistics;
+ * = T: the reference's 5-D GroupNorm over (c/g, t, h, w). `scratch` >= NF*16*groups*2 floats. */
+int mvb_op_groupnorm(const void* x0, int c0, const void* x1, int c1, int NF, int HW, int groups, int frames_per_stat,
+                     float eps, const float* gamma, const float* beta, int silu, void* y, float* scratch, void* stream);
+
+/* LayerNorm over the channel axis of [M, C] fp16 (F.layer_norm at musev/models/attention.py:193,346-350,399). */
+int mvb_op_layernorm(const void* x, long long M, int C, float eps, const float* gamma, const float* beta, void* y,
+                     void* stream);
+
+/* Fused overlap mean + classifier-free guidance + DDIM step, eta = 0
+ * (musev/pipelines/pipeline_controlnet.py:2079,2101-2117; musev/schedulers/scheduling_ddim.py:198-264).
+ * eps_sum fp32 [2B,C,T,HW] (uncond half first), counter fp32 [T], latents fp32 (is_f32) or fp16 [B,C,T,HW].
+ * prediction_type: 0 epsilon, 1 v_prediction, 2 sample. clip_range <= 0 disables clipping. eps_out may be NULL. */
+int mvb_fuse_cfg_ddim(const float* eps_sum, const float* counter, const void* latents_in, void* latents_out,
+                      int is_f32, int B, int C, int T, int HW, float guidance_scale, float alpha_prod_t,
+                      float alpha_prod_t_prev, int prediction_type, float clip_range, float* eps_out, void* stream);
+
+/* eps_sum[:, :, frames[i]] += eps_window[:, :, src_t0 + i] (musev/pipelines/pipeline_controlnet.py:2068-2078).
+ * eps_window [2B, C, Tw, HW] fp32/fp16; frames_dev: device int32[nframes]. */
+int mvb_accumulate_window(float* eps_sum, int B2, int C, int T, int HW, const void* eps_window, int is_f32, int Tw,
+                          int src_t0, const int* frames_dev, int nframes, void* stream);
+
+
+/* ---------------------------------------------------------------------------------------------------------
+ * Whole-model level: the denoiser `UNet3DConditionModel` (musev/models/unet_3d_condition.py:179-1280).
+ *
+ * mvb_config mirrors the constructor arguments that change the computation (unet_3d_condition.py:213-258) for the
+ * released presets of musev/models/unet_loader.py:232-268. One handle per device, not re-entrant (the reference is
+ * driven by a single Python thread on the default stream).
+ */
+typedef struct mvb_config {
+  int in_channels, out_channels;
+  int num_blocks;                 /* len(block_out_channels), <= 4 */
+  int block_out_channels[4];
+  int layers_per_block;
+  int heads;                      /* `attention_head_dim` of the reference config (it is the head COUNT) */
+  int cross_attention_dim;
+  int norm_num_groups;
+  float norm_eps;
+  int need_transformer_in;
+  int use_anivv1_cfg;
+  int resnet_2d_skip_time_act;
+  int keep_vision_condtion;
+  int need_refer_emb;
+  int ip_adapter_cross_attn;
+  int need_t2i_ip_adapter;        /* reference-only self attention toward the vision-condition frame(s) */
+} mvb_config;
+
+typedef struct mvb_handle mvb_handle;
+
+#define MVB_MAX_REFER 16
+/* Arguments of one `UNet3DConditionModel.forward` call (unet_3d_condition.py:773-803). Video tensors are the
+ * reference's NCTHW layout, fp16 or fp32 (flag per tensor group), contiguous. */
+typedef struct mvb_unet_args {
+  const void* sample; int sample_is_f32;       /* [B, in_channels, T, H, W], vision-condition frames included */
+  int B, T, H, W;
+  float timestep;
+  const void* encoder_hidden_states; int ehs_is_f32; int n_text;   /* [B, n_text, cross_attention_dim] */
+  int has_sample_index;                        /* sample_index is not None */
+  int n_vis_cond, vis_cond_first;              /* vision_conditon_frames_sample_index = [first, first + n) ; n = 0: None */
+  float sample_frame_rate;
+  const void* vision_clip_emb; int clip_is_f32; int n_clip; float ip_adapter_scale;  /* [B, n_clip, cross_dim] or NULL */
+  int n_refer;                                 /* 0 or the number of down_block_refer_embs */
+  const void* refer_embs[MVB_MAX_REFER]; int refer_t[MVB_MAX_REFER], refer_h[MVB_MAX_REFER], refer_w[MVB_MAX_REFER];
+  const void* mid_refer_emb; int mid_refer_t, mid_refer_h, mid_refer_w;
+  int refer_is_f32;                            /* refer maps are [B, C, t, h, w] */
+  int n_down_residuals;                        /* ControlNet: 0 or 1 + num_blocks*(layers_per_block+1) - 1 tensors */
+  const void* down_residuals[MVB_MAX_REFER];   /* [(B T), C, h, w] */
+  const void* mid_residual; int residual_is_f32;
+  int skip_temporal_layers;
+  void* out; int out_is_f32;                   /* [B, out_channels, T, H, W] */
+} mvb_unet_args;
+
+/* Reference: UNet3DConditionModel.__init__ (unet_3d_condition.py:213-610). */
+int mvb_create(const mvb_config* cfg, int device, mvb_handle** out);
+void mvb_destroy(mvb_handle* h);
+/* Reference: from_pretrained_2d / load_state_dict (unet_3d_condition.py:1284-1637): feed every tensor of the
+ * reference state_dict by its reference name; the library packs it into its kernel layout on the device. */
+int mvb_load_weight(mvb_handle* h, const char* name, const void* device_ptr, int is_f32, const long long* shape, int ndim);
+/* Checks that every tensor of the schema has been loaded. */
+int mvb_finalize(mvb_handle* h);
+int mvb_num_params(mvb_handle* h);
+/* Bytes of scratch `mvb_unet_forward` needs for these shapes (activation arena; the caller owns it). */
+long long mvb_workspace_bytes(mvb_handle* h, const mvb_unet_args* args);
+/* Reference: UNet3DConditionModel.forward (unet_3d_condition.py:773-1280). Asynchronous on `stream`. */
+int mvb_unet_forward(mvb_handle* h, const mvb_unet_args* args, void* workspace, long long workspace_bytes, void* stream);
+const char* mvb_handle_error(mvb_handle* h);
+/* Debug aid for bisecting parity: layer outputs of the last forward, fp16 [rows, C] inside the caller's workspace. */
+int mvb_debug_num_taps(mvb_handle* h);
+int mvb_debug_tap(mvb_handle* h, int i, char* name, int name_cap, const void** ptr, long long* rows, int* C);
 
 #ifdef __cplusplus
 }

@@ -27,7 +27,19 @@ class ConvGemmDesc(C.Structure):
         ("rowadd", C.c_void_p), ("rows_per_group", C.c_int), ("ld_rowadd", C.c_int),
         ("residual", C.c_void_p), ("ld_res", C.c_longlong),
         ("alpha", C.c_float), ("beta", C.c_float),
-        ("geglu", C.c_int), ("act", C.c_int),
+        ("geglu", C.c_int), ("act", C.c_int), ("out_f32", C.c_int), ("stride2", C.c_int),
+    ]
+
+
+class AttentionDesc(C.Structure):
+    _fields_ = [
+        ("q", C.c_void_p), ("ldq", C.c_longlong),
+        ("NF", C.c_int), ("Nq", C.c_int), ("heads", C.c_int), ("d", C.c_int), ("dp", C.c_int),
+        ("scale", C.c_float), ("nseg", C.c_int),
+        ("k", C.c_void_p * 2), ("v", C.c_void_p * 2), ("ldkv", C.c_longlong * 2), ("kv_rows", C.c_longlong * 2),
+        ("nk", C.c_int * 2), ("fdiv", C.c_int * 2), ("fmul", C.c_longlong * 2), ("fadd", C.c_longlong * 2),
+        ("out", C.c_void_p), ("ldo", C.c_longlong),
+        ("out_scale", C.c_float), ("accumulate", C.c_int),
     ]
 
 
@@ -49,6 +61,23 @@ def _declare(l: C.CDLL) -> None:
     l.mvb_version.restype = C.c_int
     l.mvb_op_conv_gemm.argtypes = [C.POINTER(ConvGemmDesc), C.c_void_p]
     l.mvb_op_conv_gemm.restype = C.c_int
+    l.mvb_op_attention.argtypes = [C.POINTER(AttentionDesc), C.c_void_p]
+    l.mvb_op_attention.restype = C.c_int
+    l.mvb_op_temporal_attention.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int,
+                                            C.c_float, C.c_void_p, C.c_int, C.c_void_p]
+    l.mvb_op_temporal_attention.restype = C.c_int
+    l.mvb_op_groupnorm.argtypes = [C.c_void_p, C.c_int, C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int,
+                                   C.c_float, C.c_void_p, C.c_void_p, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p]
+    l.mvb_op_groupnorm.restype = C.c_int
+    l.mvb_op_layernorm.argtypes = [C.c_void_p, C.c_longlong, C.c_int, C.c_float, C.c_void_p, C.c_void_p, C.c_void_p,
+                                   C.c_void_p]
+    l.mvb_op_layernorm.restype = C.c_int
+    l.mvb_fuse_cfg_ddim.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int,
+                                    C.c_int, C.c_float, C.c_float, C.c_float, C.c_int, C.c_float, C.c_void_p, C.c_void_p]
+    l.mvb_fuse_cfg_ddim.restype = C.c_int
+    l.mvb_accumulate_window.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_void_p, C.c_int, C.c_int,
+                                        C.c_int, C.c_void_p, C.c_int, C.c_void_p]
+    l.mvb_accumulate_window.restype = C.c_int
 
 
 def check(rc: int) -> None:

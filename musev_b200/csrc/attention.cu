@@ -1,0 +1,308 @@
+// tcgen05 flash attention (see attention.cuh). One CTA = 128 queries of one (frame, head).
+//
+//   warp 0      : TMA producer (Q once; K ring; V ring) -- boxes of 128 rows x 64 fp16, 128-byte swizzle
+//   warp 1      : TMEM allocator + single-thread MMA issuer
+//                   S = Q K^T   (M=128 queries, N=128 keys, K=dp)      -> TMEM columns [0,128)
+//                   O += P V    (M=128, N=dp, K=128 keys; V consumed MN-major straight from its row-major tile)
+//   warps 2..5  : softmax, one thread per query row: tcgen05.ld S, online max/sum with lazy rescaling of the TMEM
+//                 accumulator (only when the running max grows by > 2^8), P -> fp16 -> swizzled smem as MMA A operand
+// Two CTAs are resident per SM when the head dimension allows (dp <= 64), so one CTA's softmax overlaps the other's
+// MMAs. With d = 40 the kernel is bound by the exp throughput of the SFUs, not by the tensor pipe.
+#include "attention.cuh"
+
+#include <cuda.h>
+#include <stdio.h>
+
+#include "ptx.cuh"
+
+namespace mvb {
+
+bool encode_map_2d(CUtensorMap* m, const void* ptr, uint64_t d0, uint64_t d1, uint64_t stride1_elems, uint32_t b0,
+                   uint32_t b1);  // conv_gemm.cu
+
+struct AttnParams {
+  int NF, Nq, heads, d, dp, natoms;
+  float scale_log2, out_scale;
+  int nseg;
+  int nk[2], fdiv[2];
+  long long fmul[2], fadd[2];
+  int sk, sv;  // K / V ring depth
+  int tmem_cols;
+  __half* out;
+  long long ldo;
+  int accumulate;
+};
+
+static constexpr int kAtomBytes = 128 * 128;  // 128 rows x 64 fp16
+
+__device__ __forceinline__ void tile_info(const AttnParams& p, int j, int* seg, int* k0, int* valid) {
+  const int t0 = (p.nk[0] + 127) / 128;
+  if (j < t0) {
+    *seg = 0; *k0 = j * 128; *valid = min(128, p.nk[0] - j * 128);
+  } else {
+    *seg = 1; *k0 = (j - t0) * 128; *valid = min(128, p.nk[1] - (j - t0) * 128);
+  }
+}
+
+__global__ void __launch_bounds__(192)
+attention_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUtensorMap tmK0,
+                 const __grid_constant__ CUtensorMap tmV0, const __grid_constant__ CUtensorMap tmK1,
+                 const __grid_constant__ CUtensorMap tmV1, const __grid_constant__ AttnParams p) {
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  const int tile_bytes = p.natoms * kAtomBytes;
+  uint8_t* sQ = smem;
+  uint8_t* sK = sQ + tile_bytes;
+  uint8_t* sV = sK + p.sk * tile_bytes;
+  uint8_t* sP = sV + p.sv * tile_bytes;
+  uint64_t* bars = reinterpret_cast<uint64_t*>(sP + 2 * kAtomBytes);
+  uint64_t* bar_q = bars;          // 1
+  uint64_t* full_k = bars + 1;     // [2]
+  uint64_t* empty_k = bars + 3;    // [2]
+  uint64_t* full_v = bars + 5;     // [2]
+  uint64_t* empty_v = bars + 7;    // [2]
+  uint64_t* bar_s = bars + 9;
+  uint64_t* bar_p = bars + 10;
+  uint64_t* bar_o = bars + 11;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 12);
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int q0 = blockIdx.x * 128;
+  const int h = blockIdx.y;
+  const int f = blockIdx.z;
+  const int ntiles = (p.nk[0] + 127) / 128 + (p.nseg > 1 ? (p.nk[1] + 127) / 128 : 0);
+
+  if (warp == 0 && lane == 0) {
+    tma_prefetch_desc(&tmQ); tma_prefetch_desc(&tmK0); tma_prefetch_desc(&tmV0);
+    mbar_init(bar_q, 1);
+    for (int s = 0; s < 2; ++s) {
+      mbar_init(&full_k[s], 1); mbar_init(&empty_k[s], 1);
+      mbar_init(&full_v[s], 1); mbar_init(&empty_v[s], 1);
+    }
+    mbar_init(bar_s, 1);
+    mbar_init(bar_p, 128);
+    mbar_init(bar_o, 1);
+    fence_barrier_init();
+  }
+  if (warp == 1) {
+    tmem_alloc(tmem_slot, (uint32_t)p.tmem_cols);
+    tmem_relinquish();
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+  const uint32_t tmem_S = tmem_base;
+  const uint32_t tmem_O = tmem_base + 128;
+
+  if (warp == 0) {
+    if (lane == 0) {
+      mbar_expect_tx(bar_q, (uint32_t)tile_bytes);
+      for (int a = 0; a < p.natoms; ++a)
+        tma_load_2d(sQ + a * kAtomBytes, &tmQ, bar_q, h * p.dp + a * 64, f * p.Nq + q0);
+      for (int j = 0; j < ntiles; ++j) {
+        int seg, k0, valid;
+        tile_info(p, j, &seg, &k0, &valid);
+        const long long row = (long long)(f / p.fdiv[seg]) * p.fmul[seg] + p.fadd[seg] + k0;
+        const CUtensorMap* mk = seg ? &tmK1 : &tmK0;
+        const CUtensorMap* mv = seg ? &tmV1 : &tmV0;
+        const int ks = j % p.sk, vs = j % p.sv;
+        mbar_wait(&empty_k[ks], ((j / p.sk) & 1) ^ 1);
+        mbar_expect_tx(&full_k[ks], (uint32_t)tile_bytes);
+        for (int a = 0; a < p.natoms; ++a)
+          tma_load_2d(sK + ks * tile_bytes + a * kAtomBytes, mk, &full_k[ks], h * p.dp + a * 64, (int)row);
+        mbar_wait(&empty_v[vs], ((j / p.sv) & 1) ^ 1);
+        mbar_expect_tx(&full_v[vs], (uint32_t)tile_bytes);
+        for (int a = 0; a < p.natoms; ++a)
+          tma_load_2d(sV + vs * tile_bytes + a * kAtomBytes, mv, &full_v[vs], h * p.dp + a * 64, (int)row);
+      }
+    }
+  } else if (warp == 1) {
+    if (lane == 0) {
+      const uint32_t idesc_s = make_idesc_f16(128, 128, 0, 0);
+      const uint32_t idesc_o = make_idesc_f16(128, p.dp, 0, 1);   // B (= V) is MN-major
+      const int ksteps = p.dp / 16;
+      mbar_wait(bar_q, 0);
+      for (int j = 0; j < ntiles; ++j) {
+        const int ks = j % p.sk, vs = j % p.sv;
+        mbar_wait(&full_k[ks], (j / p.sk) & 1);
+        tc_fence_after();
+        const uint32_t aQ = smem_u32(sQ);
+        const uint32_t aK = smem_u32(sK + ks * tile_bytes);
+        for (int kk = 0; kk < ksteps; ++kk) {
+          const uint32_t off = (uint32_t)(kk >> 2) * kAtomBytes + (uint32_t)(kk & 3) * 32;
+          umma_f16_ss(tmem_S, make_desc_k_sw128(aQ + off), make_desc_k_sw128(aK + off), idesc_s, kk != 0);
+        }
+        umma_commit(&empty_k[ks]);   // K stage free once S_j is done
+        umma_commit(bar_s);
+        mbar_wait(&full_v[vs], (j / p.sv) & 1);
+        mbar_wait(bar_p, j & 1);     // P_j in smem, O rescaled
+        tc_fence_after();
+        const uint32_t aP = smem_u32(sP);
+        const uint32_t aV = smem_u32(sV + vs * tile_bytes);
+        for (int k16 = 0; k16 < 8; ++k16) {
+          const uint32_t offp = (uint32_t)(k16 >> 2) * kAtomBytes + (uint32_t)(k16 & 3) * 32;
+          umma_f16_ss(tmem_O, make_desc_k_sw128(aP + offp), make_desc_mn_sw128(aV + (uint32_t)k16 * 2048, kAtomBytes),
+                      idesc_o, (j | k16) != 0);
+        }
+        umma_commit(&empty_v[vs]);
+        if (j == ntiles - 1) umma_commit(bar_o);
+      }
+    }
+  } else {
+    const int qd = warp & 3;
+    const int row = qd * 32 + lane;
+    const uint32_t lane_off = (uint32_t)(qd * 32) << 16;
+    float m = -INFINITY, l = 0.f;
+    for (int j = 0; j < ntiles; ++j) {
+      int seg, k0, valid;
+      tile_info(p, j, &seg, &k0, &valid);
+      mbar_wait(bar_s, j & 1);
+      tc_fence_after();
+      float mx = -INFINITY;
+#pragma unroll 1
+      for (int c = 0; c < 4; ++c) {
+        uint32_t v[32];
+        tmem_ld32(tmem_S + lane_off + c * 32, v);
+        tmem_ld_wait();
+#pragma unroll
+        for (int i = 0; i < 32; ++i)
+          if (c * 32 + i < valid) mx = fmaxf(mx, __uint_as_float(v[i]));
+      }
+      mx *= p.scale_log2;
+      const bool need = mx > m + 8.f;
+      float alpha = 1.f;
+      if (need) { alpha = exp2f(m - mx); m = mx; }
+      if (j > 0 && __any_sync(0xffffffffu, need)) {
+        for (int c0 = 0; c0 < p.dp; c0 += 32) {
+          if (c0 + 32 <= p.dp) {
+            uint32_t o[32];
+            tmem_ld32(tmem_O + lane_off + c0, o);
+            tmem_ld_wait();
+#pragma unroll
+            for (int i = 0; i < 32; ++i) o[i] = __float_as_uint(__uint_as_float(o[i]) * alpha);
+            tmem_st32(tmem_O + lane_off + c0, o);
+          } else {
+            uint32_t o[16];
+            tmem_ld16(tmem_O + lane_off + c0, o);
+            tmem_ld_wait();
+#pragma unroll
+            for (int i = 0; i < 16; ++i) o[i] = __float_as_uint(__uint_as_float(o[i]) * alpha);
+            tmem_st16(tmem_O + lane_off + c0, o);
+          }
+        }
+        tmem_st_wait();
+      }
+      l *= alpha;
+#pragma unroll 1
+      for (int c = 0; c < 4; ++c) {
+        uint32_t v[32];
+        tmem_ld32(tmem_S + lane_off + c * 32, v);
+        tmem_ld_wait();
+        uint8_t* prow = sP + (c >> 1) * kAtomBytes + row * 128;
+#pragma unroll
+        for (int g = 0; g < 4; ++g) {
+          __align__(16) __half2 ph[4];
+#pragma unroll
+          for (int e = 0; e < 4; ++e) {
+            const int col = c * 32 + g * 8 + 2 * e;
+            const float p0 = (col < valid) ? exp2f(__uint_as_float(v[g * 8 + 2 * e]) * p.scale_log2 - m) : 0.f;
+            const float p1 = (col + 1 < valid) ? exp2f(__uint_as_float(v[g * 8 + 2 * e + 1]) * p.scale_log2 - m) : 0.f;
+            ph[e] = __floats2half2_rn(p0, p1);
+            const float2 back = __half22float2(ph[e]);
+            l += back.x + back.y;
+          }
+          const int chunk = (c & 1) * 4 + g;
+          *reinterpret_cast<uint4*>(prow + ((chunk ^ (row & 7)) << 4)) = *reinterpret_cast<const uint4*>(ph);
+        }
+      }
+      fence_proxy_async();
+      tc_fence_before();
+      mbar_arrive(bar_p);
+    }
+    // epilogue
+    mbar_wait(bar_o, 0);
+    tc_fence_after();
+    const float inv = p.out_scale / l;
+    const int qrow = q0 + row;
+    const bool ok = qrow < p.Nq;
+    __half* orow = p.out + ((long long)f * p.Nq + qrow) * p.ldo + h * p.d;
+    for (int c0 = 0; c0 < p.dp; c0 += 16) {
+      uint32_t o[16];
+      tmem_ld16(tmem_O + lane_off + c0, o);
+      tmem_ld_wait();
+      if (ok) {
+#pragma unroll
+        for (int g = 0; g < 2; ++g) {
+          const int cc = c0 + g * 8;
+          if (cc < p.d) {
+            __align__(16) __half oh[8];
+            if (p.accumulate) *reinterpret_cast<uint4*>(oh) = *reinterpret_cast<const uint4*>(orow + cc);
+#pragma unroll
+            for (int e = 0; e < 8; ++e) {
+              float x = __uint_as_float(o[g * 8 + e]) * inv;
+              if (p.accumulate) x += __half2float(oh[e]);
+              oh[e] = __float2half_rn(x);
+            }
+            *reinterpret_cast<uint4*>(orow + cc) = *reinterpret_cast<const uint4*>(oh);
+          }
+        }
+      }
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) tmem_dealloc(tmem_base, (uint32_t)p.tmem_cols);
+}
+
+cudaError_t launch_attention(cudaStream_t stream, const AttnArgs& a, const char** err) {
+  if (a.d % 8 || a.dp % 16 || a.dp < a.d || a.dp > 192 || a.nseg < 1 || a.nseg > 2 || a.heads < 1) {
+    *err = "attention: head dim must be a multiple of 8, padded dim a multiple of 16 (<= 192), 1..2 KV segments";
+    return cudaErrorInvalidValue;
+  }
+  AttnParams p{};
+  p.NF = a.NF; p.Nq = a.Nq; p.heads = a.heads; p.d = a.d; p.dp = a.dp;
+  p.natoms = (a.dp + 63) / 64;
+  p.scale_log2 = a.scale * 1.4426950408889634f;
+  p.out_scale = a.out_scale;
+  p.nseg = a.nseg;
+  for (int s = 0; s < 2; ++s) {
+    const AttnSegment& g = a.seg[s < a.nseg ? s : 0];
+    p.nk[s] = s < a.nseg ? g.nk : 0;
+    p.fdiv[s] = g.fdiv > 0 ? g.fdiv : 1;
+    p.fmul[s] = g.fmul; p.fadd[s] = g.fadd;
+    if (s < a.nseg && g.nk < 1) { *err = "attention: empty KV segment"; return cudaErrorInvalidValue; }
+  }
+  p.out = a.out; p.ldo = a.ldo; p.accumulate = a.accumulate;
+  if (p.natoms == 1) { p.sk = 2; p.sv = 1; }
+  else if (p.natoms == 2) { p.sk = 2; p.sv = 1; }
+  else { p.sk = 1; p.sv = 1; }
+  p.tmem_cols = (128 + a.dp <= 256) ? 256 : 512;
+  const int smem = (1 + p.sk + p.sv) * p.natoms * kAtomBytes + 2 * kAtomBytes + 1024 + 128;
+  static int max_set = 0;
+  if (smem > max_set) {
+    cudaError_t e = cudaFuncSetAttribute(attention_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
+    if (e != cudaSuccess) { *err = "cudaFuncSetAttribute(attention_kernel)"; return e; }
+    max_set = 227 * 1024;
+  }
+  CUtensorMap tq, tk0, tv0, tk1, tv1;
+  const uint64_t cols = (uint64_t)a.heads * a.dp;
+  if (!encode_map_2d(&tq, a.q, cols, (uint64_t)a.NF * a.Nq, (uint64_t)a.ldq, 64, 128)) {
+    *err = "cuTensorMapEncodeTiled(Q) failed"; return cudaErrorInvalidValue;
+  }
+  const AttnSegment& s0 = a.seg[0];
+  const AttnSegment& s1 = a.seg[a.nseg > 1 ? 1 : 0];
+  if (!encode_map_2d(&tk0, s0.k, cols, (uint64_t)s0.rows, (uint64_t)s0.ld, 64, 128) ||
+      !encode_map_2d(&tv0, s0.v, cols, (uint64_t)s0.rows, (uint64_t)s0.ld, 64, 128) ||
+      !encode_map_2d(&tk1, s1.k, cols, (uint64_t)s1.rows, (uint64_t)s1.ld, 64, 128) ||
+      !encode_map_2d(&tv1, s1.v, cols, (uint64_t)s1.rows, (uint64_t)s1.ld, 64, 128)) {
+    *err = "cuTensorMapEncodeTiled(K/V) failed"; return cudaErrorInvalidValue;
+  }
+  dim3 grid((a.Nq + 127) / 128, a.heads, a.NF);
+  attention_kernel<<<grid, 192, smem, stream>>>(tq, tk0, tv0, tk1, tv1, p);
+  cudaError_t e = cudaGetLastError();
+  if (e != cudaSuccess) *err = "attention_kernel launch";
+  return e;
+}
+
+}  // namespace mvb

@@ -5,6 +5,7 @@
 #include <string.h>
 
 #include "../../include/musev_b200.h"
+#include "attention.cuh"
 #include "conv_gemm.cuh"
 #include "ops.cuh"
 
@@ -40,11 +41,81 @@ int mvb_op_conv_gemm(const mvb_conv_gemm_desc* d, void* stream) {
   Epilogue ep;
   ep.out = (__half*)d->out; ep.ldc = d->ldc; ep.bias = d->bias; ep.rowadd = d->rowadd;
   ep.rows_per_group = d->rows_per_group; ep.ld_rowadd = d->ld_rowadd; ep.res = (const __half*)d->residual;
-  ep.ld_res = d->ld_res; ep.alpha = d->alpha; ep.beta = d->beta; ep.geglu = d->geglu; ep.act = d->act;
+  ep.ld_res = d->ld_res; ep.alpha = d->alpha; ep.beta = d->beta; ep.geglu = d->geglu; ep.act = d->act; ep.out_f32 = d->out_f32;
   const char* err = nullptr;
+  if (d->stride2) {
+    cudaError_t e2 = launch_conv_s2((cudaStream_t)stream, (const __half*)d->a0, d->c0, d->W, d->H, d->NF,
+                                    (const __half*)d->weight, d->N, ep, sm_count(), &err);
+    if (e2 != cudaSuccess) return fail(err, e2);
+    return MVB_OK;
+  }
   cudaError_t e = launch_conv_gemm((cudaStream_t)stream, a0, d->a1 ? &a1 : nullptr, d->W, d->H, d->NF, d->ntaps,
                                    d->dy, d->dx, (const __half*)d->weight, d->N, ep, sm_count(), &err);
   if (e != cudaSuccess) return fail(err, e);
+  return MVB_OK;
+}
+
+
+int mvb_op_attention(const mvb_attention_desc* d, void* stream) {
+  if (!d || !d->q || !d->out || !d->k[0] || !d->v[0]) return fail("mvb_op_attention: null pointer", cudaSuccess);
+  AttnArgs a{};
+  a.q = (const __half*)d->q; a.ldq = d->ldq; a.NF = d->NF; a.Nq = d->Nq; a.heads = d->heads; a.d = d->d; a.dp = d->dp;
+  a.scale = d->scale; a.nseg = d->nseg;
+  for (int s = 0; s < 2 && s < d->nseg; ++s) {
+    a.seg[s].k = (const __half*)d->k[s]; a.seg[s].v = (const __half*)d->v[s]; a.seg[s].ld = d->ldkv[s];
+    a.seg[s].rows = d->kv_rows[s]; a.seg[s].nk = d->nk[s]; a.seg[s].fdiv = d->fdiv[s]; a.seg[s].fmul = d->fmul[s];
+    a.seg[s].fadd = d->fadd[s];
+  }
+  a.out = (__half*)d->out; a.ldo = d->ldo; a.out_scale = d->out_scale; a.accumulate = d->accumulate;
+  const char* err = nullptr;
+  cudaError_t e = launch_attention((cudaStream_t)stream, a, &err);
+  if (e != cudaSuccess) return fail(err, e);
+  return MVB_OK;
+}
+
+int mvb_op_temporal_attention(const void* qkv, int ld, int B, int T, int HW, int heads, int d, int dp, float scale,
+                              void* out, int ldo, void* stream) {
+  cudaError_t e = temporal_attention((cudaStream_t)stream, (const __half*)qkv, ld, B, T, HW, heads, d, dp, scale,
+                                     (__half*)out, ldo);
+  if (e != cudaSuccess) return fail("mvb_op_temporal_attention", e == cudaErrorInvalidValue ? cudaSuccess : e);
+  return MVB_OK;
+}
+
+int mvb_op_groupnorm(const void* x0, int c0, const void* x1, int c1, int NF, int HW, int groups, int frames_per_stat,
+                     float eps, const float* gamma, const float* beta, int silu, void* y, float* scratch, void* stream) {
+  int chunks = 0;
+  cudaError_t e = gn_stats((cudaStream_t)stream, (const __half*)x0, c0, (const __half*)x1, c1, NF, HW, groups, scratch,
+                           &chunks);
+  if (e == cudaSuccess)
+    e = gn_apply((cudaStream_t)stream, (const __half*)x0, c0, (const __half*)x1, c1, NF, HW, groups, scratch, chunks,
+                 frames_per_stat, eps, gamma, beta, silu, (__half*)y);
+  if (e != cudaSuccess) return fail("mvb_op_groupnorm", e == cudaErrorInvalidValue ? cudaSuccess : e);
+  return MVB_OK;
+}
+
+int mvb_op_layernorm(const void* x, long long M, int C, float eps, const float* gamma, const float* beta, void* y,
+                     void* stream) {
+  cudaError_t e = layernorm((cudaStream_t)stream, (const __half*)x, M, C, eps, gamma, beta, (__half*)y);
+  if (e != cudaSuccess) return fail("mvb_op_layernorm", e == cudaErrorInvalidValue ? cudaSuccess : e);
+  return MVB_OK;
+}
+
+int mvb_fuse_cfg_ddim(const float* eps_sum, const float* counter, const void* latents_in, void* latents_out,
+                      int is_f32, int B, int C, int T, int HW, float guidance_scale, float alpha_prod_t,
+                      float alpha_prod_t_prev, int prediction_type, float clip_range, float* eps_out, void* stream) {
+  if (!eps_sum || !counter || !latents_in || !latents_out) return fail("mvb_fuse_cfg_ddim: null pointer", cudaSuccess);
+  cudaError_t e = fuse_cfg_ddim((cudaStream_t)stream, eps_sum, counter, latents_in, latents_out, is_f32, B, C, T, HW,
+                                guidance_scale, alpha_prod_t, alpha_prod_t_prev, prediction_type, clip_range, eps_out);
+  if (e != cudaSuccess) return fail("mvb_fuse_cfg_ddim", e);
+  return MVB_OK;
+}
+
+int mvb_accumulate_window(float* eps_sum, int B2, int C, int T, int HW, const void* eps_window, int is_f32, int Tw,
+                          int src_t0, const int* frames_dev, int nframes, void* stream) {
+  if (!eps_sum || !eps_window || !frames_dev) return fail("mvb_accumulate_window: null pointer", cudaSuccess);
+  cudaError_t e = accumulate_window((cudaStream_t)stream, eps_sum, B2, C, T, HW, eps_window, is_f32, Tw, src_t0,
+                                    frames_dev, nframes);
+  if (e != cudaSuccess) return fail("mvb_accumulate_window", e);
   return MVB_OK;
 }
 

@@ -30,6 +30,7 @@ __device__ __forceinline__ float silu(float x) { return x / (1.f + __expf(-x)); 
 
 __global__ void __launch_bounds__(256, 1)
 conv_gemm_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__ CUtensorMap tmA1,
+                 const __grid_constant__ CUtensorMap tmA2, const __grid_constant__ CUtensorMap tmA3,
                  const __grid_constant__ CUtensorMap tmB, const __grid_constant__ ConvGemmParams p) {
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
@@ -46,6 +47,8 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant
   if (warp == 0 && lane == 0) {
     tma_prefetch_desc(&tmA0);
     tma_prefetch_desc(&tmA1);
+    tma_prefetch_desc(&tmA2);
+    tma_prefetch_desc(&tmA3);
     tma_prefetch_desc(&tmB);
   }
   if (warp == 1 && lane == 0) {
@@ -92,10 +95,10 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant
           uint8_t* sa = smem + stage * kStageBytes;
           uint8_t* sb = sa + kABytes;
           mbar_expect_tx(&full[stage], stage_tx);
-          if (cb < p.kb0)
-            tma_load_4d(sa, &tmA0, &full[stage], cb * kBlockK, w0 + p.dx[tap], h0 + p.dy[tap], n0);
-          else
-            tma_load_4d(sa, &tmA1, &full[stage], (cb - p.kb0) * kBlockK, w0 + p.dx[tap], h0 + p.dy[tap], n0);
+          const int src = p.tap_src[tap] + (cb < p.kb0 ? 0 : 1);
+          const int c0 = (cb < p.kb0 ? cb : cb - p.kb0) * kBlockK;
+          const CUtensorMap* tm = src == 0 ? &tmA0 : (src == 1 ? &tmA1 : (src == 2 ? &tmA2 : &tmA3));
+          tma_load_4d(sa, tm, &full[stage], c0, w0 + p.dx[tap], h0 + p.dy[tap], n0);
           tma_load_2d(sb, &tmB, &full[stage], kb * kBlockK, nt * p.block_n);
           if (++stage == kStages) { stage = 0; phase ^= 1; }
         }
@@ -198,6 +201,19 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant
             if (g * 8 < ncols && nn < p.N) {
               __align__(16) __half o[8];
               float rr[8];
+              if (p.out_f32) {
+                float* dstf = reinterpret_cast<float*>(p.out) + m * p.ldc + nn;
+                float of[8];
+#pragma unroll
+                for (int j = 0; j < 8; ++j) {
+                  float x = f[g * 8 + j] * p.alpha;
+                  if (p.act == 1) x = silu(x);
+                  of[j] = x;
+                }
+                reinterpret_cast<float4*>(dstf)[0] = make_float4(of[0], of[1], of[2], of[3]);
+                reinterpret_cast<float4*>(dstf)[1] = make_float4(of[4], of[5], of[6], of[7]);
+                continue;
+              }
               if (p.res) {
                 const uint4 rv = __ldg(reinterpret_cast<const uint4*>(p.res + m * p.ld_res + nn));
                 const __half* rh8 = reinterpret_cast<const __half*>(&rv);
@@ -307,15 +323,42 @@ static int pick_block_n(int N, int geglu, long long tiles_m, int num_sms) {
   return best;
 }
 
-cudaError_t launch_conv_gemm(cudaStream_t stream, const ASource& a0, const ASource* a1, int W, int H, int NF,
-                             int ntaps, const int8_t* dy, const int8_t* dx, const __half* wt, int N,
-                             const Epilogue& ep, int num_sms, const char** err) {
+static cudaError_t launch_common(cudaStream_t stream, const CUtensorMap* maps, int nmaps, ConvGemmParams& p,
+                                 const __half* wt, long long ktot, const Epilogue& ep, int num_sms, const char** err) {
   static bool attr_set = false;
   if (!attr_set) {
     cudaError_t e = cudaFuncSetAttribute(conv_gemm_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemBytes);
     if (e != cudaSuccess) { *err = "cudaFuncSetAttribute(conv_gemm_kernel)"; return e; }
     attr_set = true;
   }
+  const long long tiles_m = (long long)p.tiles_w * p.tiles_h * p.tiles_n;
+  p.block_n = pick_block_n(p.N, ep.geglu, tiles_m, num_sms);
+  p.tiles_nn = ceil_div(p.N, p.block_n);
+  p.out = ep.out; p.ldc = ep.ldc; p.bias = ep.bias; p.rowadd = ep.rowadd;
+  p.rows_per_group = ep.rows_per_group > 0 ? ep.rows_per_group : 1;
+  p.ld_rowadd = ep.ld_rowadd; p.res = ep.res; p.ld_res = ep.ld_res; p.alpha = ep.alpha; p.beta = ep.beta;
+  p.geglu = ep.geglu; p.act = ep.act; p.out_f32 = ep.out_f32;
+  if (ep.out_f32 && (ep.geglu || ep.res)) { *err = "conv_gemm: fp32 output excludes geglu/residual"; return cudaErrorInvalidValue; }
+  CUtensorMap tmB;
+  if (!encode_map_2d(&tmB, wt, (uint64_t)ktot, (uint64_t)p.N, (uint64_t)ktot, 64u, (uint32_t)p.block_n)) {
+    *err = "cuTensorMapEncodeTiled(B) failed";
+    return cudaErrorInvalidValue;
+  }
+  const long long num_tiles = tiles_m * p.tiles_nn;
+  const int grid = (int)(num_tiles < num_sms ? num_tiles : num_sms);
+  const CUtensorMap& m0 = maps[0];
+  const CUtensorMap& m1 = maps[nmaps > 1 ? 1 : 0];
+  const CUtensorMap& m2 = maps[nmaps > 2 ? 2 : 0];
+  const CUtensorMap& m3 = maps[nmaps > 3 ? 3 : 0];
+  conv_gemm_kernel<<<grid, 256, kSmemBytes, stream>>>(m0, m1, m2, m3, tmB, p);
+  cudaError_t e = cudaGetLastError();
+  if (e != cudaSuccess) *err = "conv_gemm_kernel launch";
+  return e;
+}
+
+cudaError_t launch_conv_gemm(cudaStream_t stream, const ASource& a0, const ASource* a1, int W, int H, int NF,
+                             int ntaps, const int8_t* dy, const int8_t* dx, const __half* wt, int N,
+                             const Epilogue& ep, int num_sms, const char** err) {
   if ((a0.C % 64) || (a1 && (a1->C % 64)) || (N % 8) || ntaps < 1 || ntaps > 9) {
     *err = "conv_gemm: channels must be multiples of 64, N a multiple of 8, 1..9 taps";
     return cudaErrorInvalidValue;
@@ -325,43 +368,60 @@ cudaError_t launch_conv_gemm(cudaStream_t stream, const ASource& a0, const ASour
   pick_box(W, H, NF, &p.bw, &p.bh, &p.bn);
   p.tiles_w = ceil_div(W, p.bw); p.tiles_h = ceil_div(H, p.bh); p.tiles_n = ceil_div(NF, p.bn);
   p.ntaps = ntaps;
-  for (int i = 0; i < ntaps; ++i) { p.dy[i] = dy[i]; p.dx[i] = dx[i]; }
+  for (int i = 0; i < ntaps; ++i) { p.dy[i] = dy[i]; p.dx[i] = dx[i]; p.tap_src[i] = 0; }
   p.kb0 = a0.C / 64;
   p.kb1 = a1 ? a1->C / 64 : 0;
   p.N = N;
-  const long long tiles_m = (long long)p.tiles_w * p.tiles_h * p.tiles_n;
-  p.block_n = pick_block_n(N, ep.geglu, tiles_m, num_sms);
-  p.tiles_nn = ceil_div(N, p.block_n);
-  p.out = ep.out; p.ldc = ep.ldc; p.bias = ep.bias; p.rowadd = ep.rowadd;
-  p.rows_per_group = ep.rows_per_group > 0 ? ep.rows_per_group : 1;
-  p.ld_rowadd = ep.ld_rowadd; p.res = ep.res; p.ld_res = ep.ld_res; p.alpha = ep.alpha; p.beta = ep.beta;
-  p.geglu = ep.geglu; p.act = ep.act;
-
-  CUtensorMap tmA0, tmA1, tmB;
+  CUtensorMap maps[2];
   const uint32_t box[4] = {64u, (uint32_t)p.bw, (uint32_t)p.bh, (uint32_t)p.bn};
   {
     const uint64_t dims[4] = {(uint64_t)a0.C, (uint64_t)W, (uint64_t)H, (uint64_t)NF};
     const uint64_t st[3] = {(uint64_t)a0.sW, (uint64_t)a0.sH, (uint64_t)a0.sN};
-    if (!encode_map_4d(&tmA0, a0.ptr, dims, st, box)) { *err = "cuTensorMapEncodeTiled(A0) failed"; return cudaErrorInvalidValue; }
+    if (!encode_map_4d(&maps[0], a0.ptr, dims, st, box)) { *err = "cuTensorMapEncodeTiled(A0) failed"; return cudaErrorInvalidValue; }
   }
   if (a1) {
     const uint64_t dims[4] = {(uint64_t)a1->C, (uint64_t)W, (uint64_t)H, (uint64_t)NF};
     const uint64_t st[3] = {(uint64_t)a1->sW, (uint64_t)a1->sH, (uint64_t)a1->sN};
-    if (!encode_map_4d(&tmA1, a1->ptr, dims, st, box)) { *err = "cuTensorMapEncodeTiled(A1) failed"; return cudaErrorInvalidValue; }
-  } else {
-    tmA1 = tmA0;
+    if (!encode_map_4d(&maps[1], a1->ptr, dims, st, box)) { *err = "cuTensorMapEncodeTiled(A1) failed"; return cudaErrorInvalidValue; }
   }
   const long long ktot = (long long)ntaps * (a0.C + (a1 ? a1->C : 0));
-  if (!encode_map_2d(&tmB, wt, (uint64_t)ktot, (uint64_t)N, (uint64_t)ktot, 64u, (uint32_t)p.block_n)) {
-    *err = "cuTensorMapEncodeTiled(B) failed";
+  return launch_common(stream, maps, a1 ? 2 : 1, p, wt, ktot, ep, num_sms, err);
+}
+
+cudaError_t launch_conv_s2(cudaStream_t stream, const __half* x, int C, int W, int H, int NF, const __half* wt, int N,
+                           const Epilogue& ep, int num_sms, const char** err) {
+  if ((C % 64) || (N % 8) || (W % 2) || (H % 2)) {
+    *err = "conv_s2: channels multiple of 64, even H and W";
     return cudaErrorInvalidValue;
   }
-  const long long num_tiles = tiles_m * p.tiles_nn;
-  const int grid = (int)(num_tiles < num_sms ? num_tiles : num_sms);
-  conv_gemm_kernel<<<grid, 256, kSmemBytes, stream>>>(tmA0, tmA1, tmB, p);
-  cudaError_t e = cudaGetLastError();
-  if (e != cudaSuccess) *err = "conv_gemm_kernel launch";
-  return e;
+  const int Wo = W / 2, Ho = H / 2;
+  ConvGemmParams p{};
+  p.W = Wo; p.H = Ho; p.NF = NF;
+  pick_box(Wo, Ho, NF, &p.bw, &p.bh, &p.bn);
+  p.tiles_w = ceil_div(Wo, p.bw); p.tiles_h = ceil_div(Ho, p.bh); p.tiles_n = ceil_div(NF, p.bn);
+  p.ntaps = 9;
+  for (int ky = 0; ky < 3; ++ky)
+    for (int kx = 0; kx < 3; ++kx) {
+      const int i = ky * 3 + kx;
+      // input row 2y + ky - 1: ky=0 -> odd phase at y-1; ky=1 -> even phase at y; ky=2 -> odd phase at y
+      const int py = (ky == 1) ? 0 : 1, px = (kx == 1) ? 0 : 1;
+      p.dy[i] = (ky == 0) ? -1 : 0;
+      p.dx[i] = (kx == 0) ? -1 : 0;
+      p.tap_src[i] = (int8_t)(py * 2 + px);
+    }
+  p.kb0 = C / 64; p.kb1 = 0; p.N = N;
+  CUtensorMap maps[4];
+  const uint32_t box[4] = {64u, (uint32_t)p.bw, (uint32_t)p.bh, (uint32_t)p.bn};
+  for (int py = 0; py < 2; ++py)
+    for (int px = 0; px < 2; ++px) {
+      const uint64_t dims[4] = {(uint64_t)C, (uint64_t)Wo, (uint64_t)Ho, (uint64_t)NF};
+      const uint64_t st[3] = {(uint64_t)2 * C, (uint64_t)2 * W * C, (uint64_t)H * W * C};
+      if (!encode_map_4d(&maps[py * 2 + px], x + ((long long)py * W + px) * C, dims, st, box)) {
+        *err = "cuTensorMapEncodeTiled(phase) failed";
+        return cudaErrorInvalidValue;
+      }
+    }
+  return launch_common(stream, maps, 4, p, wt, 9LL * C, ep, num_sms, err);
 }
 
 }  // namespace mvb

@@ -23,6 +23,7 @@ struct ConvGemmParams {
   int tiles_w, tiles_h, tiles_n;
   int ntaps;
   int8_t dy[9], dx[9];
+  int8_t tap_src[9];  // tensor map used by tap i for its first kb0 blocks; the next kb1 blocks use tap_src[i]+1
   int kb0, kb1;  // 64-channel blocks contributed by source 0 / source 1 per tap
   int N;         // GEMM N (packed width; with GEGLU the written width is N/2)
   int block_n, tiles_nn;
@@ -38,6 +39,7 @@ struct ConvGemmParams {
   float alpha, beta;
   int geglu;  // packed columns are [16 value | 16 gate] chunks: out = value * gelu_erf(gate)
   int act;    // 0 none, 1 SiLU
+  int out_f32;  // store fp32 instead of fp16 (embedding tables)
 };
 
 struct ASource {
@@ -58,11 +60,18 @@ struct Epilogue {
   float alpha = 1.f, beta = 1.f;
   int geglu = 0;
   int act = 0;
+  int out_f32 = 0;
 };
 
 // Returns cudaSuccess or an error; never throws. `taps`: ntaps pairs (dy, dx).
 cudaError_t launch_conv_gemm(cudaStream_t stream, const ASource& a0, const ASource* a1, int W, int H, int NF,
                              int ntaps, const int8_t* dy, const int8_t* dx, const __half* wt, int N,
                              const Epilogue& ep, int num_sms, const char** err);
+
+// 3x3 / stride 2 / pad 1 convolution (Downsample2D, diffusers models/resnet.py:247-278) on [NF, H, W, C] with even
+// H, W: the four (row, column) parity phases of the input are four strided TMA views; every tap reads one of them
+// at offset 0 or -1, so the same kernel runs it without an im2col pass. Output image is H/2 x W/2.
+cudaError_t launch_conv_s2(cudaStream_t stream, const __half* x, int C, int W, int H, int NF, const __half* wt, int N,
+                           const Epilogue& ep, int num_sms, const char** err);
 
 }  // namespace mvb

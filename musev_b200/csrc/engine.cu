@@ -1,0 +1,940 @@
+// Engine: weight packing + the fixed launch sequence of one UNet3D forward. See engine.cuh.
+// Reference walk-through: musev/models/unet_3d_condition.py:773-1280 and musev/models/unet_3d_blocks.py.
+#include "engine.cuh"
+
+#include <math.h>
+#include <stdio.h>
+#include <string.h>
+
+#include "attention.cuh"
+#include "conv_gemm.cuh"
+#include "ops.cuh"
+
+namespace mvb {
+
+static inline int pad16(int d) { return (d + 15) / 16 * 16; }
+
+// ---------------------------------------------------------------------------------------------- packing kernels
+template <typename TSrc>
+__global__ void pack_matrix_kernel(__half* __restrict__ dst, long long ld, int rows_dst, int kdst, const TSrc* __restrict__ src,
+                                   int nsrc, int ksrc, int rowmode, int p0, int p1, int colmode, int cin, int taps) {
+  const long long total = (long long)rows_dst * kdst;
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+    const int r = (int)(i / kdst), kk = (int)(i % kdst);
+    int srow = r;
+    if (rowmode == 1) {            // pad heads: p0 = d, p1 = dp
+      const int h = r / p1, j = r % p1;
+      srow = j < p0 ? h * p0 + j : -1;
+    } else if (rowmode == 2) {     // GEGLU: chunks of [16 value | 16 gate]
+      const int chunk = r / 32, j = r % 32;
+      srow = j < 16 ? chunk * 16 + j : rows_dst / 2 + chunk * 16 + (j - 16);
+    }
+    int scol = kk;
+    if (colmode == 1) {
+      if (kk < cin * taps) { const int tap = kk / cin, c = kk % cin; scol = c * taps + tap; } else scol = -1;
+    } else if (kk >= ksrc) scol = -1;
+    float v = 0.f;
+    if (srow >= 0 && srow < nsrc && scol >= 0) v = (float)src[(long long)srow * ksrc + scol];
+    dst[(long long)r * ld + kk] = __float2half_rn(v);
+  }
+}
+template <typename TSrc>
+__global__ void pack_vec_kernel(float* __restrict__ dst, int n, const TSrc* __restrict__ src, int nsrc, int vmode) {
+  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
+    int si = i;
+    if (vmode == 2) { const int chunk = i / 32, j = i % 32; si = j < 16 ? chunk * 16 + j : n / 2 + chunk * 16 + (j - 16); }
+    dst[i] = (si < nsrc) ? (float)src[si] : 0.f;
+  }
+}
+
+// ---------------------------------------------------------------------------------------------- construction
+Engine::Engine(const mvb_config& cfg, int device) : cfg_(cfg), device_(device) {
+  heads_ = cfg.heads;
+  cudaSetDevice(device);
+  cudaDeviceGetAttribute(&num_sms_, cudaDevAttrMultiProcessorCount, device);
+  if (num_sms_ <= 0) num_sms_ = 148;
+  slab_counting_ = true;
+  slab_off_ = 0;
+  build();                                   // pass 1: count bytes
+  slab_bytes_ = slab_off_ + 4096;
+  if (cudaMalloc(&slab_, slab_bytes_) != cudaSuccess) { err_ = "cudaMalloc(weights) failed"; slab_ = nullptr; return; }
+  cudaMemset(slab_, 0, slab_bytes_);
+  slab_counting_ = false;
+  slab_off_ = 0;
+  loaders_.clear();
+  down_.clear(); up_.clear();
+  temb_total_ = femb_total_ = 0;
+  build();                                   // pass 2: assign pointers
+  cudaMalloc(&zero_idx_dev_, 64 * sizeof(int));
+  cudaMalloc(&fidx_dev_, 128 * sizeof(float));
+}
+
+Engine::~Engine() {
+  if (slab_) cudaFree(slab_);
+  if (zero_idx_dev_) cudaFree(zero_idx_dev_);
+  if (fidx_dev_) cudaFree(fidx_dev_);
+}
+
+template <typename T> T* Engine::slab(size_t n) {
+  const size_t a = (slab_off_ + 255) & ~size_t(255);
+  slab_off_ = a + n * sizeof(T);
+  return slab_counting_ ? nullptr : reinterpret_cast<T*>(slab_ + a);
+}
+
+Mat Engine::make_mat(int N, int K, bool bias) {
+  Mat m;
+  m.N = N; m.K = K;
+  m.w = slab<__half>((size_t)N * K);
+  m.bias = bias ? slab<float>(N) : nullptr;
+  return m;
+}
+Norm Engine::make_norm(const std::string& p, int C) {
+  Norm n;
+  n.C = C;
+  n.g = slab<float>(C);
+  n.b = slab<float>(C);
+  reg_vec(p + ".weight", n.g, C, C);
+  reg_vec(p + ".bias", n.b, C, C);
+  return n;
+}
+void Engine::reg_mat(const std::string& name, Mat& m, int row0, int rows_dst, int rowmode, int p0, int p1, int nsrc,
+                     int ksrc, int colmode, int cin, int taps) {
+  Loader l{};
+  l.kind = LK_MAT;
+  l.dst = m.w ? m.w + (long long)row0 * m.K : nullptr;
+  l.ld = m.K; l.rows_dst = rows_dst; l.kdst = m.K; l.rowmode = rowmode; l.p0 = p0; l.p1 = p1;
+  l.colmode = colmode; l.cin = cin; l.taps = taps; l.nsrc = nsrc; l.ksrc = ksrc;
+  loaders_[name] = l;
+}
+void Engine::reg_vec(const std::string& name, float* dst, int n, int nsrc, int vmode) {
+  Loader l{};
+  l.kind = LK_VEC; l.vdst = dst; l.vn = n; l.nsrc = nsrc; l.vmode = vmode;
+  loaders_[name] = l;
+}
+void Engine::reg_linear(const std::string& p, Mat& m, int N, int K, bool bias) {
+  m = make_mat(N, K, bias);
+  reg_mat(p + ".weight", m, 0, N, 0, 0, 0, N, K);
+  if (bias) reg_vec(p + ".bias", m.bias, N, N);
+}
+void Engine::reg_conv(const std::string& p, Mat& m, int N, int Cin, int taps) {
+  m = make_mat(N, Cin * taps, true);
+  reg_mat(p + ".weight", m, 0, N, 0, 0, 0, N, Cin * taps, taps > 1 ? 1 : 0, Cin, taps);
+  reg_vec(p + ".bias", m.bias, N, N);
+}
+
+void Engine::build_tblock(const std::string& p, TBlock& b, int C, bool cross) {
+  const int H = heads_, d = C / H, dp = pad16(d), hd = H * dp;
+  b.cross = cross;
+  b.n1 = make_norm(p + ".norm1", C);
+  b.n2 = make_norm(p + ".norm2", C);
+  b.n3 = make_norm(p + ".norm3", C);
+  b.qkv1 = make_mat(3 * hd, C, false);
+  reg_mat(p + ".attn1.to_q.weight", b.qkv1, 0, hd, 1, d, dp, C, C);
+  reg_mat(p + ".attn1.to_k.weight", b.qkv1, hd, hd, 1, d, dp, C, C);
+  reg_mat(p + ".attn1.to_v.weight", b.qkv1, 2 * hd, hd, 1, d, dp, C, C);
+  reg_linear(p + ".attn1.to_out.0", b.out1, C, C, true);
+  if (cross) {
+    const int X = cfg_.cross_attention_dim;
+    b.q2 = make_mat(hd, C, false);
+    reg_mat(p + ".attn2.to_q.weight", b.q2, 0, hd, 1, d, dp, C, C);
+    b.kv2 = make_mat(2 * hd, X, false);
+    reg_mat(p + ".attn2.to_k.weight", b.kv2, 0, hd, 1, d, dp, C, X);
+    reg_mat(p + ".attn2.to_v.weight", b.kv2, hd, hd, 1, d, dp, C, X);
+    b.has_ip = cfg_.ip_adapter_cross_attn != 0;
+    if (b.has_ip) {
+      b.kv2_ip = make_mat(2 * hd, X, false);
+      reg_mat(p + ".attn2.to_k_ip.weight", b.kv2_ip, 0, hd, 1, d, dp, C, X);
+      reg_mat(p + ".attn2.to_v_ip.weight", b.kv2_ip, hd, hd, 1, d, dp, C, X);
+    }
+  } else {
+    b.qkv2 = make_mat(3 * hd, C, false);
+    reg_mat(p + ".attn2.to_q.weight", b.qkv2, 0, hd, 1, d, dp, C, C);
+    reg_mat(p + ".attn2.to_k.weight", b.qkv2, hd, hd, 1, d, dp, C, C);
+    reg_mat(p + ".attn2.to_v.weight", b.qkv2, 2 * hd, hd, 1, d, dp, C, C);
+  }
+  reg_linear(p + ".attn2.to_out.0", b.out2, C, C, true);
+  b.ff1 = make_mat(8 * C, C, true);
+  reg_mat(p + ".ff.net.0.proj.weight", b.ff1, 0, 8 * C, 2, 0, 0, 8 * C, C);
+  reg_vec(p + ".ff.net.0.proj.bias", b.ff1.bias, 8 * C, 8 * C, 2);
+  reg_linear(p + ".ff.net.2", b.ff2, C, 4 * C, true);
+}
+
+void Engine::build_resnet(const std::string& p, Resnet& r, int cin, int C) {
+  r.cin = cin; r.C = C;
+  r.n1 = make_norm(p + ".norm1", cin);
+  reg_conv(p + ".conv1", r.conv1, C, cin, 9);
+  r.temb_off = temb_total_;
+  reg_mat(p + ".time_emb_proj.weight", temb_all_, temb_total_, C, 0, 0, 0, C, cfg_.block_out_channels[0] * 4);
+  reg_vec(p + ".time_emb_proj.bias", temb_all_.bias ? temb_all_.bias + temb_total_ : nullptr, C, C);
+  temb_total_ += C;
+  r.n2 = make_norm(p + ".norm2", C);
+  reg_conv(p + ".conv2", r.conv2, C, C, 9);
+  r.has_shortcut = cin != C;
+  if (r.has_shortcut) reg_conv(p + ".conv_shortcut", r.shortcut, C, cin, 1);
+}
+void Engine::build_tempconv(const std::string& p, TempConv& t, int C) {
+  t.C = C;
+  static const int ci[4] = {2, 3, 3, 3};
+  for (int i = 0; i < 4; ++i) {
+    const std::string q = p + ".conv" + std::to_string(i + 1);
+    t.n[i] = make_norm(q + ".0", C);
+    reg_conv(q + "." + std::to_string(ci[i]), t.conv[i], C, C, 3);
+  }
+  Loader l{};
+  l.kind = LK_ABS_SCALAR; l.host_scalar = &t.tw;
+  loaders_[p + ".temporal_weight"] = l;
+}
+void Engine::build_spatial(const std::string& p, SpatialT& s, int C) {
+  s.C = C;
+  s.norm = make_norm(p + ".norm", C);
+  reg_conv(p + ".proj_in", s.proj_in, C, C, 1);
+  build_tblock(p + ".transformer_blocks.0", s.blk, C, true);
+  reg_conv(p + ".proj_out", s.proj_out, C, C, 1);
+}
+void Engine::build_temporal(const std::string& p, TemporalT& t, int C) {
+  t.C = C;
+  Loader l{};
+  l.kind = LK_ABS_SCALAR; l.host_scalar = &t.tw;
+  loaders_[p + ".temporal_weight"] = l;
+  t.norm = make_norm(p + ".norm", C);
+  reg_linear(p + ".proj_in", t.proj_in, C, C, true);
+  t.femb_off = femb_total_;
+  reg_mat(p + ".frame_emb_proj.weight", femb_all_, femb_total_, C, 0, 0, 0, C, cfg_.block_out_channels[0] * 4);
+  reg_vec(p + ".frame_emb_proj.bias", femb_all_.bias ? femb_all_.bias + femb_total_ : nullptr, C, C);
+  femb_total_ += C;
+  build_tblock(p + ".transformer_blocks.0", t.blk, C, false);
+  reg_linear(p + ".proj_out", t.proj_out, C, C, true);
+}
+void Engine::build_refer(const std::string& p, ReferAttn& r, int C) {
+  const int H = heads_, d = C / H, dp = pad16(d), hd = H * dp;
+  r.C = C; r.present = true;
+  r.qkv = make_mat(3 * hd, C, false);
+  reg_mat(p + ".to_q.weight", r.qkv, 0, hd, 1, d, dp, C, C);
+  reg_mat(p + ".to_k.weight", r.qkv, hd, hd, 1, d, dp, C, C);
+  reg_mat(p + ".to_v.weight", r.qkv, 2 * hd, hd, 1, d, dp, C, C);
+  reg_linear(p + ".to_out.0", r.out, C, C, true);
+}
+
+void Engine::build() {
+  const mvb_config& c = cfg_;
+  const int nb = c.num_blocks;
+  const int c0 = c.block_out_channels[0], temb = 4 * c0;
+  // count the concatenated embedding projections first (their size is needed before the layers register rows)
+  int n_res_c = 0, n_tt_c = 0;
+  {
+    int ch = c0;
+    for (int i = 0; i < nb; ++i) {
+      ch = c.block_out_channels[i];
+      n_res_c += c.layers_per_block * ch;
+      if (i != nb - 1) n_tt_c += c.layers_per_block * ch;
+    }
+    n_res_c += 2 * c.block_out_channels[nb - 1];
+    n_tt_c += c.block_out_channels[nb - 1];
+    for (int i = 0; i < nb; ++i) {
+      const int chh = c.block_out_channels[nb - 1 - i];
+      n_res_c += (c.layers_per_block + 1) * chh;
+      if (i > 0) n_tt_c += (c.layers_per_block + 1) * chh;
+    }
+    if (c.need_transformer_in) n_tt_c += c0;
+  }
+  temb_all_ = make_mat(n_res_c, temb, true);
+  femb_all_ = make_mat(n_tt_c, temb, true);
+  temb_total_ = femb_total_ = 0;
+
+  conv_in_ = make_mat(c0, 64, true);
+  reg_mat("conv_in.weight", conv_in_, 0, c0, 0, 0, 0, c0, c.in_channels * 9, 1, c.in_channels, 9);
+  reg_vec("conv_in.bias", conv_in_.bias, c0, c0);
+  reg_linear("time_embedding.linear_1", time_l1_, temb, c0, true);
+  reg_linear("time_embedding.linear_2", time_l2_, temb, temb, true);
+  reg_linear("frame_embedding.linear_1", frame_l1_, temb, c0, true);
+  reg_linear("frame_embedding.linear_2", frame_l2_, temb, temb, true);
+  has_tin_ = c.need_transformer_in != 0;
+  if (has_tin_) build_temporal("transformer_in", tin_, c0);
+  if (c.need_refer_emb) {
+    build_refer("first_refer_emb_attns", first_ref_, c0);
+    build_refer("mid_block_refer_emb_attns", mid_ref_, c.block_out_channels[nb - 1]);
+  }
+  down_.resize(nb);
+  int ch = c0;
+  for (int i = 0; i < nb; ++i) {
+    const int cin = ch;
+    ch = c.block_out_channels[i];
+    const bool final = i == nb - 1;
+    Block& b = down_[i];
+    b.layers.resize(c.layers_per_block);
+    const std::string p = "down_blocks." + std::to_string(i);
+    for (int j = 0; j < c.layers_per_block; ++j) {
+      Layer& L = b.layers[j];
+      build_resnet(p + ".resnets." + std::to_string(j), L.res, j == 0 ? cin : ch, ch);
+      build_tempconv(p + ".temp_convs." + std::to_string(j), L.tc, ch);
+      L.has_attn = !final;
+      if (L.has_attn) {
+        build_spatial(p + ".attentions." + std::to_string(j), L.st, ch);
+        build_temporal(p + ".temp_attentions." + std::to_string(j), L.tt, ch);
+      }
+      if (c.need_refer_emb) build_refer(p + ".refer_emb_attns." + std::to_string(j), L.ref, ch);
+    }
+    b.has_sampler = !final;
+    if (!final) {
+      reg_conv(p + ".downsamplers.0.conv", b.sampler, ch, ch, 9);
+      if (c.need_refer_emb) build_refer(p + ".refer_emb_attns." + std::to_string(c.layers_per_block), b.ref_down, ch);
+    }
+  }
+  const int cm = c.block_out_channels[nb - 1];
+  build_resnet("mid_block.resnets.0", mid_res_[0], cm, cm);
+  build_tempconv("mid_block.temp_convs.0", mid_tc_[0], cm);
+  build_spatial("mid_block.attentions.0", mid_st_, cm);
+  build_temporal("mid_block.temp_attentions.0", mid_tt_, cm);
+  build_resnet("mid_block.resnets.1", mid_res_[1], cm, cm);
+  build_tempconv("mid_block.temp_convs.1", mid_tc_[1], cm);
+  up_.resize(nb);
+  ch = cm;
+  for (int i = 0; i < nb; ++i) {
+    const int prev = ch;
+    ch = c.block_out_channels[nb - 1 - i];
+    const int cin_block = c.block_out_channels[nb - 1 - (i + 1 < nb ? i + 1 : nb - 1)];
+    const bool final = i == nb - 1;
+    Block& b = up_[i];
+    b.layers.resize(c.layers_per_block + 1);
+    const std::string p = "up_blocks." + std::to_string(i);
+    for (int j = 0; j <= c.layers_per_block; ++j) {
+      Layer& L = b.layers[j];
+      const int skip = (j == c.layers_per_block) ? cin_block : ch;
+      const int rin = (j == 0) ? prev : ch;
+      build_resnet(p + ".resnets." + std::to_string(j), L.res, rin + skip, ch);
+      build_tempconv(p + ".temp_convs." + std::to_string(j), L.tc, ch);
+      L.has_attn = i > 0;
+      if (L.has_attn) {
+        build_spatial(p + ".attentions." + std::to_string(j), L.st, ch);
+        build_temporal(p + ".temp_attentions." + std::to_string(j), L.tt, ch);
+      }
+    }
+    b.has_sampler = !final;
+    if (!final) reg_conv(p + ".upsamplers.0.conv", b.sampler, ch, ch, 9);
+  }
+  norm_out_ = make_norm("conv_norm_out", c0);
+  conv_out_ = make_mat(16, 9 * c0, true);
+  reg_mat("conv_out.weight", conv_out_, 0, 16, 0, 0, 0, c.out_channels, 9 * c0, 1, c0, 9);
+  reg_vec("conv_out.bias", conv_out_.bias, 16, c.out_channels);
+}
+
+int Engine::load_weight(const char* name, const void* ptr, int is_f32, const long long* shape, int ndim) {
+  if (!slab_) { err_ = "engine not initialised"; return MVB_ERR_STATE; }
+  auto it = loaders_.find(name);
+  if (it == loaders_.end()) { err_ = std::string("unexpected weight name: ") + name; return MVB_ERR_INVALID; }
+  Loader& l = it->second;
+  long long numel = 1;
+  for (int i = 0; i < ndim; ++i) numel *= shape[i];
+  cudaSetDevice(device_);
+  if (l.kind == LK_ABS_SCALAR) {
+    if (numel != 1) { err_ = std::string("bad shape for ") + name; return MVB_ERR_INVALID; }
+    float v = 0.f;
+    if (is_f32) cudaMemcpy(&v, ptr, sizeof(float), cudaMemcpyDeviceToHost);
+    else { __half hv; cudaMemcpy(&hv, ptr, sizeof(__half), cudaMemcpyDeviceToHost); v = __half2float(hv); }
+    *l.host_scalar = fabsf(v);   // the reference applies torch.abs (musev/models/resnet.py:128, temporal_transformer.py:299)
+  } else if (l.kind == LK_VEC) {
+    if (numel != l.nsrc) { err_ = std::string("bad shape for ") + name; return MVB_ERR_INVALID; }
+    const int blocks = (l.vn + 255) / 256;
+    if (is_f32) pack_vec_kernel<float><<<blocks, 256>>>(l.vdst, l.vn, (const float*)ptr, l.nsrc, l.vmode);
+    else pack_vec_kernel<__half><<<blocks, 256>>>(l.vdst, l.vn, (const __half*)ptr, l.nsrc, l.vmode);
+  } else {
+    if (numel != (long long)l.nsrc * l.ksrc) { err_ = std::string("bad shape for ") + name; return MVB_ERR_INVALID; }
+    const long long total = (long long)l.rows_dst * l.kdst;
+    const int blocks = (int)((total + 255) / 256 < 148 * 32 ? (total + 255) / 256 : 148 * 32);
+    if (is_f32)
+      pack_matrix_kernel<float><<<blocks, 256>>>(l.dst, l.ld, l.rows_dst, l.kdst, (const float*)ptr, l.nsrc, l.ksrc,
+                                                 l.rowmode, l.p0, l.p1, l.colmode, l.cin, l.taps);
+    else
+      pack_matrix_kernel<__half><<<blocks, 256>>>(l.dst, l.ld, l.rows_dst, l.kdst, (const __half*)ptr, l.nsrc, l.ksrc,
+                                                  l.rowmode, l.p0, l.p1, l.colmode, l.cin, l.taps);
+  }
+  cudaError_t e = cudaGetLastError();
+  if (e != cudaSuccess) { err_ = std::string("pack kernel: ") + cudaGetErrorString(e); return MVB_ERR_CUDA; }
+  l.loaded = true;
+  return MVB_OK;
+}
+
+int Engine::finalize() {
+  for (auto& kv : loaders_)
+    if (!kv.second.loaded) { err_ = "missing weight: " + kv.first; return MVB_ERR_STATE; }
+  cudaError_t e = cudaDeviceSynchronize();
+  if (e != cudaSuccess) { err_ = std::string("finalize: ") + cudaGetErrorString(e); return MVB_ERR_CUDA; }
+  finalized_ = true;
+  return MVB_OK;
+}
+
+// ---------------------------------------------------------------------------------------------- forward
+struct Engine::Fwd {
+  Engine* E;
+  Arena* ar;
+  cudaStream_t s;
+  bool dry;
+  const mvb_unet_args* a;
+  int B, T, H, W, NF;
+  int heads;
+  float* gn_part;           // GroupNorm partial sums scratch
+  const float* temb_table;  // [NF, temb_total] fp32
+  const float* femb_table;  // [NF, femb_total] fp32
+  const __half* enc;        // [B*n_text, X] fp16
+  const __half* clip;       // [B*n_clip, X] fp16 or null
+  bool skip_temporal;
+  bool ok = true;
+
+  bool fail(const char* what, cudaError_t e) {
+    if (ok) {
+      char buf[400];
+      snprintf(buf, sizeof(buf), "%s: %s", what ? what : "error", e == cudaSuccess ? "failed" : cudaGetErrorString(e));
+      E->err_ = buf;
+    }
+    ok = false;
+    return false;
+  }
+  __half* alloc_h(long long rows, int C) {
+    void* p = ar->alloc((size_t)rows * C * sizeof(__half));
+    if (!p) fail("workspace too small", cudaSuccess);
+    return (__half*)p;
+  }
+  float* alloc_f(long long n) {
+    void* p = ar->alloc((size_t)n * sizeof(float));
+    if (!p) fail("workspace too small", cudaSuccess);
+    return (float*)p;
+  }
+  void tap(const std::string& name, const __half* p, long long rows, int C) {
+    if (!dry) E->taps_.push_back({name, p, rows, C});
+  }
+  size_t mark() const { return ar->off; }
+  void release(size_t m) { ar->off = m; }
+
+  // ---- op wrappers (skipped in dry mode)
+  void gemm_img(const ASource& a0, const ASource* a1, int Wd, int Hd, int NFd, int ntaps, const int8_t* dy,
+                const int8_t* dx, const Mat& m, Epilogue ep, bool use_bias = true) {
+    if (!ok || dry) return;
+    if (use_bias && !ep.bias) ep.bias = m.bias;
+    const char* err = nullptr;
+    cudaError_t e = launch_conv_gemm(s, a0, a1, Wd, Hd, NFd, ntaps, dy, dx, m.w, m.N, ep, E->num_sms_, &err);
+    if (e != cudaSuccess) fail(err, e);
+  }
+  // plain GEMM: out[M, N] = x[M, K] * W^T
+  void gemm(const __half* x, long long M, int K, const Mat& m, Epilogue ep, bool use_bias = true) {
+    static const int8_t z = 0;
+    ASource a0{x, K, (long long)K, (long long)K * M, (long long)K * M};
+    if (m.K != K) { fail("gemm: K mismatch", cudaSuccess); return; }
+    gemm_img(a0, nullptr, (int)M, 1, 1, 1, &z, &z, m, ep, use_bias);
+  }
+  void conv3x3(const __half* x0, int C0, const __half* x1, int C1, int NFd, int Hd, int Wd, const Mat& m, Epilogue ep) {
+    static const int8_t dy[9] = {-1, -1, -1, 0, 0, 0, 1, 1, 1}, dx[9] = {-1, 0, 1, -1, 0, 1, -1, 0, 1};
+    ASource a0{x0, C0, (long long)C0, (long long)C0 * Wd, (long long)C0 * Wd * Hd};
+    ASource a1{x1, C1, (long long)C1, (long long)C1 * Wd, (long long)C1 * Wd * Hd};
+    gemm_img(a0, x1 ? &a1 : nullptr, Wd, Hd, NFd, 9, dy, dx, m, ep);
+  }
+  void conv1x1(const __half* x0, int C0, const __half* x1, int C1, long long M, const Mat& m, Epilogue ep) {
+    static const int8_t z = 0;
+    ASource a0{x0, C0, (long long)C0, (long long)C0 * M, (long long)C0 * M};
+    ASource a1{x1, C1, (long long)C1, (long long)C1 * M, (long long)C1 * M};
+    gemm_img(a0, x1 ? &a1 : nullptr, (int)M, 1, 1, 1, &z, &z, m, ep);
+  }
+  // temporal (3,1,1) conv over [B, T, HW, C]
+  void tconv(const __half* x, int C, int HW, const Mat& m, Epilogue ep) {
+    static const int8_t dy[3] = {-1, 0, 1}, dx[3] = {0, 0, 0};
+    ASource a0{x, C, (long long)C, (long long)C * HW, (long long)C * HW * T};
+    gemm_img(a0, nullptr, HW, T, B, 3, dy, dx, m, ep);
+  }
+  void gn(const __half* x0, int C0, const __half* x1, int C1, int HW, int fps, float eps, const Norm& n, int silu,
+          __half* y) {
+    if (!ok || dry) return;
+    int chunks = 0;
+    cudaError_t e = gn_stats(s, x0, C0, x1, C1, NF, HW, E->cfg_.norm_num_groups, gn_part, &chunks);
+    if (e == cudaSuccess)
+      e = gn_apply(s, x0, C0, x1, C1, NF, HW, E->cfg_.norm_num_groups, gn_part, chunks, fps, eps, n.g, n.b, silu, y);
+    if (e != cudaSuccess) fail("groupnorm", e);
+  }
+  void ln(const __half* x, long long M, int C, float eps, const Norm& n, __half* y) {
+    if (!ok || dry) return;
+    cudaError_t e = layernorm(s, x, M, C, eps, n.g, n.b, y);
+    if (e != cudaSuccess) fail("layernorm", e);
+  }
+  void attn(const AttnArgs& aa) {
+    if (!ok || dry) return;
+    const char* err = nullptr;
+    cudaError_t e = launch_attention(s, aa, &err);
+    if (e != cudaSuccess) fail(err, e);
+  }
+
+  // ---- layers
+  // ResnetBlock2D (diffusers models/resnet.py:696-770); x1 = skip connection concatenated on the channel axis
+  __half* resnet(const Resnet& r, const __half* x, int Cx, const __half* x1, int C1, int Hd, int Wd) {
+    const long long M = (long long)NF * Hd * Wd;
+    __half* out = alloc_h(M, r.C);
+    const size_t mk = mark();
+    __half* h0 = alloc_h(M, r.cin);
+    gn(x, Cx, x1, C1, Hd * Wd, 1, E->cfg_.norm_eps, r.n1, 1, h0);
+    __half* h1 = alloc_h(M, r.C);
+    Epilogue e1;
+    e1.out = h1; e1.ldc = r.C; e1.rowadd = temb_table + r.temb_off; e1.rows_per_group = Hd * Wd; e1.ld_rowadd = E->temb_total_;
+    conv3x3(h0, r.cin, nullptr, 0, NF, Hd, Wd, r.conv1, e1);
+    __half* h2 = h0;  // reuse (cin >= C is not guaranteed) -> allocate when it does not fit
+    if (r.cin < r.C) h2 = alloc_h(M, r.C);
+    gn(h1, r.C, nullptr, 0, Hd * Wd, 1, E->cfg_.norm_eps, r.n2, 1, h2);
+    const __half* sc = x;
+    if (r.has_shortcut) {
+      __half* scb = alloc_h(M, r.C);
+      Epilogue es;
+      es.out = scb; es.ldc = r.C;
+      conv1x1(x, Cx, x1, C1, M, r.shortcut, es);
+      sc = scb;
+    } else if (x1) {
+      fail("resnet: concat input without shortcut", cudaSuccess);
+    }
+    Epilogue e2;
+    e2.out = out; e2.ldc = r.C; e2.res = sc; e2.ld_res = r.C;
+    conv3x3(h2, r.C, nullptr, 0, NF, Hd, Wd, r.conv2, e2);
+    release(mk);
+    return out;
+  }
+  // TemporalConvLayer (musev/models/resnet.py:95-135)
+  __half* temp_conv(const TempConv& t, const __half* x, int HW) {
+    if (skip_temporal) return const_cast<__half*>(x);
+    const long long M = (long long)NF * HW;
+    __half* out = alloc_h(M, t.C);
+    const size_t mk = mark();
+    __half* nbuf = alloc_h(M, t.C);
+    __half* v0 = alloc_h(M, t.C);
+    __half* v1 = alloc_h(M, t.C);
+    const __half* cur = x;
+    for (int i = 0; i < 4; ++i) {
+      gn(cur, t.C, nullptr, 0, HW, T, 1e-5f, t.n[i], 1, nbuf);
+      Epilogue ep;
+      if (i == 3) { ep.out = out; ep.alpha = t.tw; ep.res = x; ep.ld_res = t.C; }
+      else ep.out = (i & 1) ? v1 : v0;
+      ep.ldc = t.C;
+      tconv(nbuf, t.C, HW, t.conv[i], ep);
+      cur = ep.out;
+    }
+    release(mk);
+    return out;
+  }
+  // GEGLU feed-forward + residual (diffusers models/attention.py:342-395)
+  void feed_forward(const TBlock& b, __half* h, long long M, int C, __half* nbuf) {
+    const size_t mk = mark();
+    ln(h, M, C, 0.f, b.n3, nbuf);
+    __half* ff = alloc_h(M, 4 * C);
+    Epilogue e1;
+    e1.out = ff; e1.ldc = 4 * C; e1.geglu = 1;
+    gemm(nbuf, M, C, b.ff1, e1);
+    Epilogue e2;
+    e2.out = h; e2.ldc = C; e2.res = h; e2.ld_res = C;
+    gemm(ff, M, 4 * C, b.ff2, e2);
+    release(mk);
+  }
+  // musev Transformer2DModel (transformer_2d.py:257-389) + BasicTransformerBlock (attention.py:172-431)
+  __half* spatial(const SpatialT& st, const __half* x, int HW) {
+    const int C = st.C, Hh = heads, d = C / Hh, dp = pad16(d), hd = Hh * dp;
+    const long long M = (long long)NF * HW;
+    __half* out = alloc_h(M, C);
+    const size_t mk = mark();
+    __half* nbuf = alloc_h(M, C);
+    __half* h = alloc_h(M, C);
+    gn(x, C, nullptr, 0, HW, 1, 1e-6f, st.norm, 0, nbuf);
+    { Epilogue ep; ep.out = h; ep.ldc = C; gemm(nbuf, M, C, st.proj_in, ep); }
+    const TBlock& b = st.blk;
+    // attn1: reference-only self attention
+    {
+      const size_t mk2 = mark();
+      ln(h, M, C, 0.f, b.n1, nbuf);
+      __half* qkv = alloc_h(M, 3 * hd);
+      { Epilogue ep; ep.out = qkv; ep.ldc = 3 * hd; gemm(nbuf, M, C, b.qkv1, ep, false); }
+      __half* ao = alloc_h(M, C);
+      AttnArgs aa{};
+      aa.q = qkv; aa.ldq = 3 * hd; aa.NF = NF; aa.Nq = HW; aa.heads = Hh; aa.d = d; aa.dp = dp;
+      aa.scale = 1.f / sqrtf((float)d);
+      aa.nseg = 1;
+      aa.seg[0] = AttnSegment{qkv + hd, qkv + 2 * hd, 3 * hd, M, HW, 1, HW, 0};
+      if (E->cfg_.need_t2i_ip_adapter && a->n_vis_cond > 0 && T > 1) {
+        aa.nseg = 2;
+        aa.seg[1] = AttnSegment{qkv + hd, qkv + 2 * hd, 3 * hd, M, a->n_vis_cond * HW, T, (long long)T * HW,
+                                (long long)a->vis_cond_first * HW};
+      }
+      aa.out = ao; aa.ldo = C; aa.out_scale = 1.f;
+      attn(aa);
+      Epilogue ep; ep.out = h; ep.ldc = C; ep.res = h; ep.ld_res = C;
+      gemm(ao, M, C, b.out1, ep);
+      release(mk2);
+    }
+    // attn2: text cross attention (+ IP-Adapter image tokens)
+    {
+      const size_t mk2 = mark();
+      ln(h, M, C, 1e-5f, b.n2, nbuf);
+      __half* q = alloc_h(M, hd);
+      { Epilogue ep; ep.out = q; ep.ldc = hd; gemm(nbuf, M, C, b.q2, ep, false); }
+      const int X = E->cfg_.cross_attention_dim;
+      const long long Mt = (long long)B * a->n_text;
+      __half* kv = alloc_h(Mt, 2 * hd);
+      { Epilogue ep; ep.out = kv; ep.ldc = 2 * hd; gemm(enc, Mt, X, b.kv2, ep, false); }
+      __half* ao = alloc_h(M, C);
+      AttnArgs aa{};
+      aa.q = q; aa.ldq = hd; aa.NF = NF; aa.Nq = HW; aa.heads = Hh; aa.d = d; aa.dp = dp;
+      aa.scale = 1.f / sqrtf((float)d);
+      aa.nseg = 1;
+      aa.seg[0] = AttnSegment{kv, kv + hd, 2 * hd, Mt, a->n_text, T, a->n_text, 0};
+      aa.out = ao; aa.ldo = C; aa.out_scale = 1.f;
+      attn(aa);
+      if (b.has_ip && clip && a->ip_adapter_scale > 0.f) {
+        const long long Mc = (long long)B * a->n_clip;
+        __half* kvi = alloc_h(Mc, 2 * hd);
+        { Epilogue ep; ep.out = kvi; ep.ldc = 2 * hd; gemm(clip, Mc, X, b.kv2_ip, ep, false); }
+        aa.seg[0] = AttnSegment{kvi, kvi + hd, 2 * hd, Mc, a->n_clip, T, a->n_clip, 0};
+        aa.out_scale = a->ip_adapter_scale; aa.accumulate = 1;
+        attn(aa);
+      }
+      Epilogue ep; ep.out = h; ep.ldc = C; ep.res = h; ep.ld_res = C;
+      gemm(ao, M, C, b.out2, ep);
+      release(mk2);
+    }
+    feed_forward(b, h, M, C, nbuf);
+    { Epilogue ep; ep.out = out; ep.ldc = C; ep.res = x; ep.ld_res = C; gemm(h, M, C, st.proj_out, ep); }
+    release(mk);
+    return out;
+  }
+  // TransformerTemporalModel (musev/models/temporal_transformer.py:189-308)
+  __half* temporal(const TemporalT& tt, const __half* x, int HW) {
+    if (skip_temporal) return const_cast<__half*>(x);
+    const int C = tt.C, Hh = heads, d = C / Hh, dp = pad16(d), hd = Hh * dp;
+    const long long M = (long long)NF * HW;
+    __half* out = alloc_h(M, C);
+    const size_t mk = mark();
+    __half* nbuf = alloc_h(M, C);
+    __half* h = alloc_h(M, C);
+    gn(x, C, nullptr, 0, HW, T, 1e-6f, tt.norm, 0, nbuf);
+    {
+      Epilogue ep;
+      ep.out = h; ep.ldc = C; ep.rowadd = femb_table + tt.femb_off; ep.rows_per_group = HW; ep.ld_rowadd = E->femb_total_;
+      gemm(nbuf, M, C, tt.proj_in, ep);
+    }
+    const TBlock& b = tt.blk;
+    for (int which = 0; which < 2; ++which) {
+      const size_t mk2 = mark();
+      ln(h, M, C, which == 0 ? 0.f : 1e-5f, which == 0 ? b.n1 : b.n2, nbuf);
+      __half* qkv = alloc_h(M, 3 * hd);
+      { Epilogue ep; ep.out = qkv; ep.ldc = 3 * hd; gemm(nbuf, M, C, which == 0 ? b.qkv1 : b.qkv2, ep, false); }
+      __half* ao = alloc_h(M, C);
+      if (ok && !dry) {
+        cudaError_t e = temporal_attention(s, qkv, 3 * hd, B, T, HW, Hh, d, dp, 1.f / sqrtf((float)d), ao, C);
+        if (e != cudaSuccess) fail("temporal_attention", e);
+      }
+      Epilogue ep; ep.out = h; ep.ldc = C; ep.res = h; ep.ld_res = C;
+      gemm(ao, M, C, which == 0 ? b.out1 : b.out2, ep);
+      release(mk2);
+    }
+    feed_forward(b, h, M, C, nbuf);
+    { Epilogue ep; ep.out = out; ep.ldc = C; ep.alpha = tt.tw; ep.res = x; ep.ld_res = C; gemm(h, M, C, tt.proj_out, ep); }
+    release(mk);
+    return out;
+  }
+  // ReferEmbFuseAttention (musev/models/attention_processor.py:629-750); ref tokens [B*nref, C]
+  __half* refer_fuse(const ReferAttn& r, const __half* x, int HW, const __half* ref, int nref) {
+    const int C = r.C, Hh = heads, d = C / Hh, dp = pad16(d), hd = Hh * dp;
+    const long long M = (long long)NF * HW;
+    __half* out = alloc_h(M, C);
+    const size_t mk = mark();
+    __half* qkv = alloc_h(M, 3 * hd);
+    { Epilogue ep; ep.out = qkv; ep.ldc = 3 * hd; gemm(x, M, C, r.qkv, ep, false); }
+    const long long Mr = (long long)B * nref;
+    __half* kvr = alloc_h(Mr, 2 * hd);
+    {
+      Mat kvw = r.qkv;
+      kvw.w = r.qkv.w ? r.qkv.w + (long long)hd * C : nullptr;
+      kvw.N = 2 * hd;
+      Epilogue ep; ep.out = kvr; ep.ldc = 2 * hd;
+      gemm(ref, Mr, C, kvw, ep, false);
+    }
+    __half* ao = alloc_h(M, C);
+    AttnArgs aa{};
+    aa.q = qkv; aa.ldq = 3 * hd; aa.NF = NF; aa.Nq = HW; aa.heads = Hh; aa.d = d; aa.dp = dp;
+    aa.scale = 1.f / sqrtf((float)d);
+    aa.nseg = 2;
+    aa.seg[0] = AttnSegment{kvr, kvr + hd, 2 * hd, Mr, nref, T, nref, 0};
+    aa.seg[1] = AttnSegment{qkv + hd, qkv + 2 * hd, 3 * hd, M, HW, 1, HW, 0};
+    aa.out = ao; aa.ldo = C; aa.out_scale = 1.f;
+    attn(aa);
+    Epilogue ep; ep.out = out; ep.ldc = C; ep.res = x; ep.ld_res = C;
+    gemm(ao, M, C, r.out, ep);
+    release(mk);
+    return out;
+  }
+  // reference feature map [B, C, t, h, w] -> tokens [B*t*h*w, C]
+  __half* refer_tokens(const void* map, int C, int t, int h, int w) {
+    __half* tok = alloc_h((long long)B * t * h * w, C);
+    if (ok && !dry) {
+      cudaError_t e = ncthw_to_tokens(s, map, a->refer_is_f32, B, C, t, h * w, tok, C, 1.f);
+      if (e != cudaSuccess) fail("refer tokens", e);
+    }
+    return tok;
+  }
+};
+
+bool Engine::run(const mvb_unet_args& a, Arena& ar, cudaStream_t s) {
+  const mvb_config& c = cfg_;
+  Fwd f;
+  f.E = this; f.ar = &ar; f.s = s; f.dry = ar.dry; f.a = &a;
+  f.B = a.B; f.T = a.T; f.H = a.H; f.W = a.W; f.NF = a.B * a.T;
+  f.heads = heads_;
+  f.skip_temporal = a.skip_temporal_layers != 0;
+  const int nb = c.num_blocks, c0 = c.block_out_channels[0], temb = 4 * c0;
+  const int B = a.B, T = a.T, NF = f.NF;
+  if (a.H % (1 << (nb - 1)) || a.W % (1 << (nb - 1))) { err_ = "H and W must be divisible by 2^(num_blocks-1)"; return false; }
+  if (T > 32) { err_ = "at most 32 frames per window (temporal attention kernel)"; return false; }
+  if (a.n_vis_cond < 0 || a.vis_cond_first < 0 || a.vis_cond_first + a.n_vis_cond > T) { err_ = "bad vision condition index range"; return false; }
+  if (c.need_refer_emb && a.n_refer != 0) {
+    int expect = 1;
+    for (int i = 0; i < nb; ++i) expect += c.layers_per_block + (i == nb - 1 ? 0 : 1);
+    if (a.n_refer != expect) { err_ = "down_block_refer_embs: wrong number of maps"; return false; }
+  }
+  if (!ar.dry) taps_.clear();
+  f.gn_part = f.alloc_f((long long)NF * kGnMaxChunks * c.norm_num_groups * 2);
+
+  // ---- embeddings (unet_3d_condition.py:887-937)
+  __half* temb_rows = f.alloc_h(NF, temb);
+  __half* femb_rows = f.alloc_h(NF, temb);
+  float* temb_table = f.alloc_f((long long)NF * temb_total_);
+  float* femb_table = f.alloc_f((long long)NF * femb_total_);
+  f.temb_table = temb_table; f.femb_table = femb_table;
+  {
+    const size_t mk = f.mark();
+    __half* sin_t = f.alloc_h(B, c0);
+    __half* e1 = f.alloc_h(B, temb);
+    __half* e2 = f.alloc_h(B, temb);
+    __half* sin_f = f.alloc_h(T, c0);
+    __half* f1 = f.alloc_h(T, temb);
+    __half* f2 = f.alloc_h(T, temb);
+    if (!ar.dry) {
+      float vals[128];
+      for (int i = 0; i < B && i < 64; ++i) vals[i] = a.timestep;
+      for (int t = 0; t < T; ++t) {
+        float fi = (float)t;
+        if (c.use_anivv1_cfg) fi = (float)(long long)((float)t * a.sample_frame_rate);   // .to(torch.long) truncation
+        vals[64 + t] = fi;
+      }
+      int zidx[64];
+      for (int i = 0; i < a.n_vis_cond && i < 64; ++i) zidx[i] = a.vis_cond_first + i;
+      cudaMemcpyAsync(fidx_dev_, vals, sizeof(float) * 128, cudaMemcpyHostToDevice, s);
+      cudaMemcpyAsync(zero_idx_dev_, zidx, sizeof(int) * 64, cudaMemcpyHostToDevice, s);
+      if (sinusoid(s, fidx_dev_, B, c0, sin_t, c0) != cudaSuccess) f.fail("sinusoid", cudaGetLastError());
+      if (sinusoid(s, fidx_dev_ + 64, T, c0, sin_f, c0) != cudaSuccess) f.fail("sinusoid", cudaGetLastError());
+    }
+    { Epilogue ep; ep.out = e1; ep.ldc = temb; ep.act = 1; f.gemm(sin_t, B, c0, time_l1_, ep); }
+    { Epilogue ep; ep.out = e2; ep.ldc = temb; ep.act = c.use_anivv1_cfg ? 1 : 0; f.gemm(e1, B, temb, time_l2_, ep); }
+    { Epilogue ep; ep.out = f1; ep.ldc = temb; ep.act = 1; f.gemm(sin_f, T, c0, frame_l1_, ep); }
+    { Epilogue ep; ep.out = f2; ep.ldc = temb; ep.act = c.use_anivv1_cfg ? 1 : 0; f.gemm(f1, T, temb, frame_l2_, ep); }
+    if (!ar.dry && f.ok) {
+      const bool zero_vc = c.keep_vision_condtion && T > 1 && a.has_sample_index && a.n_vis_cond > 0;
+      // rows of time_emb_proj input: [silu](emb) per frame, vision-condition frames zeroed (Q7)
+      cudaError_t e = expand_rows(s, e2, B, T, temb, zero_idx_dev_, zero_vc ? a.n_vis_cond : 0,
+                                  c.resnet_2d_skip_time_act ? 0 : 1, temb_rows);
+      if (e != cudaSuccess) f.fail("expand_rows(temb)", e);
+      // rows of frame_emb_proj input: SiLU(femb[t]) for every batch (temporal_transformer.py:247-251)
+      for (int b = 0; b < B && f.ok; ++b) {
+        e = silu_copy(s, f2, (long long)T * temb, femb_rows + (long long)b * T * temb);
+        if (e != cudaSuccess) f.fail("silu(femb)", e);
+      }
+    }
+    { Epilogue ep; ep.out = (__half*)temb_table; ep.ldc = temb_total_; ep.out_f32 = 1; f.gemm(temb_rows, NF, temb, temb_all_, ep); }
+    { Epilogue ep; ep.out = (__half*)femb_table; ep.ldc = femb_total_; ep.out_f32 = 1; f.gemm(femb_rows, NF, temb, femb_all_, ep); }
+    f.release(mk);
+  }
+  // ---- conditioning tokens
+  const int X = c.cross_attention_dim;
+  __half* enc = f.alloc_h((long long)B * a.n_text, X);
+  __half* clip = nullptr;
+  if (!ar.dry && f.ok) {
+    // [B, n, X] row-major is already a token matrix: view as NCTHW with C=1? -> plain convert
+    cudaError_t e = ncthw_to_tokens(s, a.encoder_hidden_states, a.ehs_is_f32, 1, 1, 1, B * a.n_text * X, enc, 1, 1.f);
+    if (e != cudaSuccess) f.fail("encoder_hidden_states convert", e);
+  }
+  if (c.ip_adapter_cross_attn && a.vision_clip_emb && a.n_clip > 0) {
+    clip = f.alloc_h((long long)B * a.n_clip, X);
+    if (!ar.dry && f.ok) {
+      cudaError_t e = ncthw_to_tokens(s, a.vision_clip_emb, a.clip_is_f32, 1, 1, 1, B * a.n_clip * X, clip, 1, 1.f);
+      if (e != cudaSuccess) f.fail("vision_clip_emb convert", e);
+    }
+  }
+  f.enc = enc; f.clip = clip;
+
+  // ---- conv_in (unet_3d_condition.py:1008-1009)
+  int Hc = a.H, Wc = a.W;
+  long long M = (long long)NF * Hc * Wc;
+  __half* x = f.alloc_h(M, c0);
+  {
+    const size_t mk = f.mark();
+    __half* A = f.alloc_h(M, 64);
+    if (!ar.dry && f.ok) {
+      cudaError_t e = im2col_latent(s, a.sample, a.sample_is_f32, B, c.in_channels, T, Hc, Wc, A);
+      if (e != cudaSuccess) f.fail("im2col_latent", e);
+    }
+    Epilogue ep; ep.out = x; ep.ldc = c0;
+    f.gemm(A, M, 64, conv_in_, ep);
+    f.release(mk);
+  }
+  f.tap("conv_in", x, M, c0);
+  if (has_tin_) { x = f.temporal(tin_, x, Hc * Wc); f.tap("transformer_in", x, M, c0); }
+  const bool use_ref = c.need_refer_emb && a.n_refer > 0;
+  if (use_ref) {
+    __half* tok = f.refer_tokens(a.refer_embs[0], c0, a.refer_t[0], a.refer_h[0], a.refer_w[0]);
+    x = f.refer_fuse(first_ref_, x, Hc * Wc, tok, a.refer_t[0] * a.refer_h[0] * a.refer_w[0]);
+    f.tap("first_refer", x, M, c0);
+  }
+  // ---- down
+  struct Skip { __half* p; int C, H, W; };
+  std::vector<Skip> skips;
+  skips.push_back({x, c0, Hc, Wc});
+  int ch = c0;
+  for (int i = 0; i < nb; ++i) {
+    const bool final = i == nb - 1;
+    Block& blk = down_[i];
+    const int num_block = c.layers_per_block + (final ? 0 : 1);
+    const int ref_start = 1 + num_block * i;     // Q19: uses this block's count for the slice start
+    for (int j = 0; j < c.layers_per_block; ++j) {
+      Layer& L = blk.layers[j];
+      const std::string pn = "down_blocks." + std::to_string(i);
+      const long long Ml = (long long)NF * Hc * Wc;
+      x = f.resnet(L.res, x, ch, nullptr, 0, Hc, Wc);
+      ch = L.res.C;
+      f.tap(pn + ".resnets." + std::to_string(j), x, Ml, ch);
+      x = f.temp_conv(L.tc, x, Hc * Wc);
+      f.tap(pn + ".temp_convs." + std::to_string(j), x, Ml, ch);
+      if (L.has_attn) {
+        x = f.spatial(L.st, x, Hc * Wc);
+        f.tap(pn + ".attentions." + std::to_string(j), x, Ml, ch);
+        x = f.temporal(L.tt, x, Hc * Wc);
+        f.tap(pn + ".temp_attentions." + std::to_string(j), x, Ml, ch);
+      }
+      if (use_ref) {
+        const int ri = ref_start + j;
+        if (ri >= a.n_refer) { err_ = "refer emb index out of range"; return false; }
+        __half* tok = f.refer_tokens(a.refer_embs[ri], ch, a.refer_t[ri], a.refer_h[ri], a.refer_w[ri]);
+        x = f.refer_fuse(L.ref, x, Hc * Wc, tok, a.refer_t[ri] * a.refer_h[ri] * a.refer_w[ri]);
+        f.tap(pn + ".refer_emb_attns." + std::to_string(j), x, Ml, ch);
+      }
+      skips.push_back({x, ch, Hc, Wc});
+    }
+    if (!final) {
+      __half* y = f.alloc_h((long long)NF * (Hc / 2) * (Wc / 2), ch);
+      if (!ar.dry && f.ok) {
+        Epilogue ep; ep.out = y; ep.ldc = ch; ep.bias = blk.sampler.bias;
+        const char* err = nullptr;
+        cudaError_t e = launch_conv_s2(s, x, ch, Wc, Hc, NF, blk.sampler.w, ch, ep, num_sms_, &err);
+        if (e != cudaSuccess) f.fail(err, e);
+      }
+      x = y; Hc /= 2; Wc /= 2;
+      if (use_ref) {
+        const int ri = ref_start + c.layers_per_block;
+        __half* tok = f.refer_tokens(a.refer_embs[ri], ch, a.refer_t[ri], a.refer_h[ri], a.refer_w[ri]);
+        x = f.refer_fuse(blk.ref_down, x, Hc * Wc, tok, a.refer_t[ri] * a.refer_h[ri] * a.refer_w[ri]);
+      }
+      f.tap("down_blocks." + std::to_string(i) + ".down", x, (long long)NF * Hc * Wc, ch);
+      skips.push_back({x, ch, Hc, Wc});
+    }
+  }
+  // ---- mid (unet_3d_blocks.py:364-433)
+  x = f.resnet(mid_res_[0], x, ch, nullptr, 0, Hc, Wc);
+  x = f.temp_conv(mid_tc_[0], x, Hc * Wc);
+  x = f.spatial(mid_st_, x, Hc * Wc);
+  x = f.temporal(mid_tt_, x, Hc * Wc);
+  x = f.resnet(mid_res_[1], x, ch, nullptr, 0, Hc, Wc);
+  x = f.temp_conv(mid_tc_[1], x, Hc * Wc);
+  f.tap("mid", x, (long long)NF * Hc * Wc, ch);
+  if (c.need_refer_emb && a.mid_refer_emb) {
+    __half* tok = f.refer_tokens(a.mid_refer_emb, ch, a.mid_refer_t, a.mid_refer_h, a.mid_refer_w);
+    x = f.refer_fuse(mid_ref_, x, Hc * Wc, tok, a.mid_refer_t * a.mid_refer_h * a.mid_refer_w);
+  }
+  // ControlNet residuals (unet_3d_condition.py:1146-1156,1195-1196). The down path and the mid block have already
+  // consumed the un-modified tensors, so the skips can be updated in place.
+  if (a.n_down_residuals > 0) {
+    if (a.n_down_residuals != (int)skips.size()) { err_ = "down_block_additional_residuals: wrong count"; return false; }
+    if (!ar.dry && f.ok)
+      for (size_t k = 0; k < skips.size(); ++k) {
+        cudaError_t e = add_nchw_residual(s, skips[k].p, NF, skips[k].C, skips[k].H * skips[k].W, a.down_residuals[k],
+                                          a.residual_is_f32);
+        if (e != cudaSuccess) { f.fail("down residual", e); break; }
+      }
+  }
+  if (a.mid_residual) {
+    // x may alias the last skip when temporal layers are skipped -> copy first
+    __half* y = f.alloc_h((long long)NF * Hc * Wc, ch);
+    if (!ar.dry && f.ok) {
+      cudaMemcpyAsync(y, x, (size_t)NF * Hc * Wc * ch * sizeof(__half), cudaMemcpyDeviceToDevice, s);
+      cudaError_t e = add_nchw_residual(s, y, NF, ch, Hc * Wc, a.mid_residual, a.residual_is_f32);
+      if (e != cudaSuccess) f.fail("mid residual", e);
+    }
+    x = y;
+  }
+  // ---- up
+  for (int i = 0; i < nb; ++i) {
+    Block& blk = up_[i];
+    const bool final = i == nb - 1;
+    for (int j = 0; j <= c.layers_per_block; ++j) {
+      Layer& L = blk.layers[j];
+      const Skip sk = skips.back();
+      skips.pop_back();
+      if (sk.H != Hc || sk.W != Wc) { err_ = "skip shape mismatch"; return false; }
+      x = f.resnet(L.res, x, ch, sk.p, sk.C, Hc, Wc);
+      ch = L.res.C;
+      x = f.temp_conv(L.tc, x, Hc * Wc);
+      if (L.has_attn) {
+        x = f.spatial(L.st, x, Hc * Wc);
+        x = f.temporal(L.tt, x, Hc * Wc);
+      }
+      f.tap("up_blocks." + std::to_string(i) + "." + std::to_string(j), x, (long long)NF * Hc * Wc, ch);
+    }
+    if (!final) {
+      // Upsample2D: nearest x2 then 3x3 conv (diffusers models/resnet.py:167-210)
+      __half* y = f.alloc_h((long long)NF * 4 * Hc * Wc, ch);
+      const size_t mk = f.mark();
+      __half* up = f.alloc_h((long long)NF * 4 * Hc * Wc, ch);
+      if (!ar.dry && f.ok) {
+        cudaError_t e = upsample2x(s, x, NF, Hc, Wc, ch, up);
+        if (e != cudaSuccess) f.fail("upsample2x", e);
+      }
+      Hc *= 2; Wc *= 2;
+      Epilogue ep; ep.out = y; ep.ldc = ch;
+      f.conv3x3(up, ch, nullptr, 0, NF, Hc, Wc, blk.sampler, ep);
+      f.release(mk);
+      x = y;
+      f.tap("up_blocks." + std::to_string(i) + ".up", x, (long long)NF * Hc * Wc, ch);
+    }
+  }
+  // ---- out (unet_3d_condition.py:1258-1263)
+  M = (long long)NF * Hc * Wc;
+  {
+    __half* hn = f.alloc_h(M, c0);
+    f.gn(x, c0, nullptr, 0, Hc * Wc, 1, c.norm_eps, norm_out_, 1, hn);
+    __half* o16 = f.alloc_h(M, 16);
+    Epilogue ep; ep.out = o16; ep.ldc = 16;
+    f.conv3x3(hn, c0, nullptr, 0, NF, Hc, Wc, conv_out_, ep);
+    if (!ar.dry && f.ok) {
+      cudaError_t e = tokens_to_ncthw(s, o16, 16, B, c.out_channels, T, Hc * Wc, a.out, a.out_is_f32);
+      if (e != cudaSuccess) f.fail("tokens_to_ncthw", e);
+    }
+  }
+  return f.ok;
+}
+
+long long Engine::workspace_bytes(const mvb_unet_args& a) {
+  Arena ar;
+  ar.dry = true;
+  if (!run(a, ar, nullptr)) return -1;
+  return (long long)ar.peak + 4096;
+}
+
+int Engine::forward(const mvb_unet_args& a, void* workspace, long long wbytes, cudaStream_t stream) {
+  if (!finalized_) { err_ = "mvb_finalize has not been called (or weights are missing)"; return MVB_ERR_STATE; }
+  if (!a.sample || !a.out || !a.encoder_hidden_states || !workspace) { err_ = "null pointer argument"; return MVB_ERR_INVALID; }
+  cudaSetDevice(device_);
+  Arena ar;
+  ar.dry = false;
+  ar.base = (char*)workspace;
+  ar.cap = (size_t)wbytes;
+  if (!run(a, ar, stream)) return MVB_ERR_CUDA;
+  return MVB_OK;
+}
+
+}  // namespace mvb

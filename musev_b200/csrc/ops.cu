@@ -1,0 +1,595 @@
+// HBM-bound kernels (see ops.cuh). Design rules: 128-bit loads/stores on the contiguous channel axis, fp32
+// statistics, grids sized to cover >= 2 waves of the 148 SMs where the tensor is large enough.
+#include "ops.cuh"
+
+#include <math.h>
+
+namespace mvb {
+
+__device__ __forceinline__ float silu_f(float x) { return x / (1.f + __expf(-x)); }
+
+struct alignas(16) Half8 {
+  __half2 h[4];
+};
+
+// ------------------------------------------------------------------------------------------------ GroupNorm
+// grid (chunks, NF); block 256. Thread owns a fixed 8-channel vector column and strides over pixels, so its
+// per-group accumulators stay in registers; groups are even-sized, so a half2 never straddles two groups.
+__global__ void __launch_bounds__(256)
+gn_stats_kernel(const __half* __restrict__ x0, int C0, const __half* __restrict__ x1, int C1, int HW, int G,
+                float* __restrict__ part) {
+  extern __shared__ float sacc[];  // [G][2]
+  const int C = C0 + C1;
+  const int vecs = C / 8;
+  const int cpg = C / G;
+  const int f = blockIdx.y;
+  const int chunks = gridDim.x;
+  for (int i = threadIdx.x; i < 2 * G; i += blockDim.x) sacc[i] = 0.f;
+  __syncthreads();
+  const int cols_per_pass = vecs < (int)blockDim.x ? vecs : (int)blockDim.x;
+  const int rows_per_iter = blockDim.x / cols_per_pass;
+  const int r0 = threadIdx.x / cols_per_pass;
+  const int p_begin = (int)(((long long)HW * blockIdx.x) / chunks);
+  const int p_end = (int)(((long long)HW * (blockIdx.x + 1)) / chunks);
+  for (int v0 = 0; v0 < vecs; v0 += cols_per_pass) {
+    const int v = v0 + threadIdx.x % cols_per_pass;
+    if (r0 < rows_per_iter && v < vecs) {
+      const int c = v * 8;
+      const __half* src = (c < C0) ? x0 + (size_t)f * HW * C0 + c : x1 + (size_t)f * HW * C1 + (c - C0);
+      const int ld = (c < C0) ? C0 : C1;
+      float s[4] = {0, 0, 0, 0}, q[4] = {0, 0, 0, 0};
+      for (int p = p_begin + r0; p < p_end; p += rows_per_iter) {
+        const Half8 hv = *reinterpret_cast<const Half8*>(src + (size_t)p * ld);
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+          const float2 t = __half22float2(hv.h[j]);
+          s[j] += t.x + t.y;
+          q[j] += t.x * t.x + t.y * t.y;
+        }
+      }
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        const int g = (c + 2 * j) / cpg;
+        atomicAdd(&sacc[2 * g], s[j]);
+        atomicAdd(&sacc[2 * g + 1], q[j]);
+      }
+    }
+  }
+  __syncthreads();
+  for (int i = threadIdx.x; i < 2 * G; i += blockDim.x)
+    part[((size_t)f * chunks + blockIdx.x) * 2 * G + i] = sacc[i];
+}
+
+cudaError_t gn_stats(cudaStream_t s, const __half* x0, int C0, const __half* x1, int C1, int NF, int HW, int G,
+                     float* part, int* chunks_out) {
+  const int C = C0 + (x1 ? C1 : 0);
+  if (!x1) C1 = 0;
+  if ((C0 % 8) || (C1 % 8) || (C % G) || ((C / G) % 2)) return cudaErrorInvalidValue;
+  const int threads = 256;
+  // enough blocks for ~2 waves, at least ~64 pixels per block
+  int chunks = (2 * 148 + NF - 1) / NF;
+  const int maxc = HW / 64 > 0 ? HW / 64 : 1;
+  if (chunks > maxc) chunks = maxc;
+  if (chunks > kGnMaxChunks) chunks = kGnMaxChunks;
+  if (chunks < 1) chunks = 1;
+  *chunks_out = chunks;
+  gn_stats_kernel<<<dim3(chunks, NF), threads, 2 * G * sizeof(float), s>>>(x0, C0, x1, C1, HW, G, part);
+  return cudaGetLastError();
+}
+
+// grid (pixel blocks, NF); block 256. Block prologue reduces the partials of its stat group into smem mean/rstd.
+__global__ void __launch_bounds__(256)
+gn_apply_kernel(const __half* __restrict__ x0, int C0, const __half* __restrict__ x1, int C1, int HW, int G,
+                const float* __restrict__ part, int chunks, int fps, float eps, const float* __restrict__ gamma,
+                const float* __restrict__ beta, int silu, __half* __restrict__ y, int pix_per_block) {
+  extern __shared__ float sm_gn[];  // mean[G], rstd[G]
+  const int C = C0 + C1;
+  const int cpg = C / G;
+  const int f = blockIdx.y;
+  const int f0 = (f / fps) * fps;
+  for (int g = threadIdx.x; g < G; g += blockDim.x) {
+    float s = 0.f, q = 0.f;
+    for (int ff = 0; ff < fps; ++ff)
+      for (int ch = 0; ch < chunks; ++ch) {
+        const float* pp = part + ((size_t)(f0 + ff) * chunks + ch) * 2 * G + 2 * g;
+        s += pp[0];
+        q += pp[1];
+      }
+    const float n = (float)fps * HW * cpg;
+    const float mean = s / n;
+    float var = q / n - mean * mean;
+    var = var < 0.f ? 0.f : var;
+    sm_gn[g] = mean;
+    sm_gn[G + g] = rsqrtf(var + eps);
+  }
+  __syncthreads();
+  const int vecs = C / 8;
+  const int p0 = blockIdx.x * pix_per_block;
+  const int p1 = min(HW, p0 + pix_per_block);
+  const int total = (p1 - p0) * vecs;
+  for (int i = threadIdx.x; i < total; i += blockDim.x) {
+    const int p = p0 + i / vecs;
+    const int c = (i % vecs) * 8;
+    const __half* src = (c < C0) ? x0 + ((size_t)f * HW + p) * C0 + c : x1 + ((size_t)f * HW + p) * C1 + (c - C0);
+    const Half8 hv = *reinterpret_cast<const Half8*>(src);
+    Half8 ov;
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      const int cc = c + 2 * j;
+      const int g = cc / cpg;
+      const float mean = sm_gn[g], rstd = sm_gn[G + g];
+      float2 t = __half22float2(hv.h[j]);
+      t.x = (t.x - mean) * rstd * __ldg(gamma + cc) + __ldg(beta + cc);
+      t.y = (t.y - mean) * rstd * __ldg(gamma + cc + 1) + __ldg(beta + cc + 1);
+      if (silu) { t.x = silu_f(t.x); t.y = silu_f(t.y); }
+      ov.h[j] = __floats2half2_rn(t.x, t.y);
+    }
+    *reinterpret_cast<Half8*>(y + ((size_t)f * HW + p) * C + c) = ov;
+  }
+}
+
+cudaError_t gn_apply(cudaStream_t s, const __half* x0, int C0, const __half* x1, int C1, int NF, int HW, int G,
+                     const float* part, int chunks, int fps, float eps, const float* gamma, const float* beta, int silu,
+                     __half* y) {
+  if (!x1) C1 = 0;
+  const int C = C0 + C1;
+  if (fps < 1 || (NF % fps)) return cudaErrorInvalidValue;
+  // ~16 KB of fp16 per block
+  int ppb = (8192 + C - 1) / C;
+  if (ppb < 1) ppb = 1;
+  const int blocks = (HW + ppb - 1) / ppb;
+  gn_apply_kernel<<<dim3(blocks, NF), 256, 2 * G * sizeof(float), s>>>(x0, C0, x1, C1, HW, G, part, chunks, fps, eps,
+                                                                       gamma, beta, silu, y, ppb);
+  return cudaGetLastError();
+}
+
+// ------------------------------------------------------------------------------------------------ LayerNorm
+// one warp per row; C <= 2560 (10 Half8 per lane)
+template <int VPL>
+__global__ void __launch_bounds__(256)
+layernorm_kernel(const __half* __restrict__ x, long long M, int C, float eps, const float* __restrict__ gamma,
+                 const float* __restrict__ beta, __half* __restrict__ y) {
+  const long long row = (long long)blockIdx.x * (blockDim.x / 32) + (threadIdx.x >> 5);
+  if (row >= M) return;
+  const int lane = threadIdx.x & 31;
+  const int vecs = C / 8;
+  float v[VPL][8];
+  float s = 0.f;
+#pragma unroll
+  for (int i = 0; i < VPL; ++i) {
+    const int vi = lane + i * 32;
+    if (vi < vecs) {
+      const Half8 hv = *reinterpret_cast<const Half8*>(x + row * C + vi * 8);
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        const float2 t = __half22float2(hv.h[j]);
+        v[i][2 * j] = t.x; v[i][2 * j + 1] = t.y;
+        s += t.x + t.y;
+      }
+    }
+  }
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
+  const float mean = s / C;
+  float q = 0.f;
+#pragma unroll
+  for (int i = 0; i < VPL; ++i) {
+    const int vi = lane + i * 32;
+    if (vi < vecs) {
+#pragma unroll
+      for (int j = 0; j < 8; ++j) { const float d = v[i][j] - mean; q += d * d; }
+    }
+  }
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) q += __shfl_xor_sync(0xffffffffu, q, o);
+  const float rstd = rsqrtf(q / C + eps);
+#pragma unroll
+  for (int i = 0; i < VPL; ++i) {
+    const int vi = lane + i * 32;
+    if (vi < vecs) {
+      Half8 ov;
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        const int c = vi * 8 + 2 * j;
+        const float a = (v[i][2 * j] - mean) * rstd * __ldg(gamma + c) + __ldg(beta + c);
+        const float b = (v[i][2 * j + 1] - mean) * rstd * __ldg(gamma + c + 1) + __ldg(beta + c + 1);
+        ov.h[j] = __floats2half2_rn(a, b);
+      }
+      *reinterpret_cast<Half8*>(y + row * C + vi * 8) = ov;
+    }
+  }
+}
+
+cudaError_t layernorm(cudaStream_t s, const __half* x, long long M, int C, float eps, const float* gamma,
+                      const float* beta, __half* y) {
+  if (C % 8) return cudaErrorInvalidValue;
+  const int vecs = C / 8;
+  const int rows_per_block = 8;
+  const unsigned blocks = (unsigned)((M + rows_per_block - 1) / rows_per_block);
+  if (vecs <= 32) layernorm_kernel<1><<<blocks, 256, 0, s>>>(x, M, C, eps, gamma, beta, y);
+  else if (vecs <= 64) layernorm_kernel<2><<<blocks, 256, 0, s>>>(x, M, C, eps, gamma, beta, y);
+  else if (vecs <= 160) layernorm_kernel<5><<<blocks, 256, 0, s>>>(x, M, C, eps, gamma, beta, y);
+  else if (vecs <= 320) layernorm_kernel<10><<<blocks, 256, 0, s>>>(x, M, C, eps, gamma, beta, y);
+  else return cudaErrorInvalidValue;
+  return cudaGetLastError();
+}
+
+// ------------------------------------------------------------------------------------------------ layout / elementwise
+__global__ void upsample2x_kernel(const __half* __restrict__ x, int H, int W, int C, __half* __restrict__ y,
+                                  long long total_vecs) {
+  const int vecs = C / 8;
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total_vecs;
+       i += (long long)gridDim.x * blockDim.x) {
+    const int v = (int)(i % vecs);
+    long long p = i / vecs;
+    const int ox = (int)(p % (2 * W)); p /= (2 * W);
+    const int oy = (int)(p % (2 * H));
+    const long long f = p / (2 * H);
+    const Half8 hv = *reinterpret_cast<const Half8*>(x + (((size_t)f * H + oy / 2) * W + ox / 2) * C + v * 8);
+    *reinterpret_cast<Half8*>(y + i * 8) = hv;
+  }
+}
+cudaError_t upsample2x(cudaStream_t s, const __half* x, int NF, int H, int W, int C, __half* y) {
+  if (C % 8) return cudaErrorInvalidValue;
+  const long long total = (long long)NF * 4 * H * W * (C / 8);
+  const int blocks = (int)((total + 255) / 256 < 148 * 16 ? (total + 255) / 256 : 148 * 16);
+  upsample2x_kernel<<<blocks, 256, 0, s>>>(x, H, W, C, y, total);
+  return cudaGetLastError();
+}
+
+__global__ void add_kernel(const __half* __restrict__ a, const __half* __restrict__ b, long long nvec,
+                           __half* __restrict__ y) {
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < nvec; i += (long long)gridDim.x * blockDim.x) {
+    const Half8 x = reinterpret_cast<const Half8*>(a)[i];
+    const Half8 z = reinterpret_cast<const Half8*>(b)[i];
+    Half8 o;
+#pragma unroll
+    for (int j = 0; j < 4; ++j) o.h[j] = __hadd2(x.h[j], z.h[j]);
+    reinterpret_cast<Half8*>(y)[i] = o;
+  }
+}
+cudaError_t add_tensors(cudaStream_t s, const __half* a, const __half* b, long long n, __half* y) {
+  if (n % 8) return cudaErrorInvalidValue;
+  const long long nv = n / 8;
+  const int blocks = (int)((nv + 255) / 256 < 148 * 16 ? (nv + 255) / 256 : 148 * 16);
+  add_kernel<<<blocks, 256, 0, s>>>(a, b, nv, y);
+  return cudaGetLastError();
+}
+
+__global__ void silu_kernel(const __half* __restrict__ x, long long n, __half* __restrict__ y) {
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x)
+    y[i] = __float2half_rn(silu_f(__half2float(x[i])));
+}
+cudaError_t silu_copy(cudaStream_t s, const __half* x, long long n, __half* y) {
+  const int blocks = (int)((n + 255) / 256 < 1024 ? (n + 255) / 256 : 1024);
+  silu_kernel<<<blocks, 256, 0, s>>>(x, n, y);
+  return cudaGetLastError();
+}
+
+// NCTHW -> tokens. Tile transpose through smem: block handles 32 pixels x up to 32 channels.
+template <typename TIn>
+__global__ void ncthw_to_tokens_kernel(const TIn* __restrict__ x, int B, int C, int T, int HW, __half* __restrict__ y,
+                                       int ldy, float scale) {
+  __shared__ float tile[32][33];
+  const int bt = blockIdx.z;
+  const int b = bt / T, t = bt % T;
+  const int p0 = blockIdx.x * 32, c0 = blockIdx.y * 32;
+  for (int cy = threadIdx.y; cy < 32; cy += blockDim.y) {
+    const int c = c0 + cy, p = p0 + threadIdx.x;
+    if (c < C && p < HW) tile[cy][threadIdx.x] = (float)x[(((size_t)b * C + c) * T + t) * HW + p];
+  }
+  __syncthreads();
+  for (int py = threadIdx.y; py < 32; py += blockDim.y) {
+    const int p = p0 + py, c = c0 + threadIdx.x;
+    if (c < C && p < HW) y[((size_t)bt * HW + p) * ldy + c] = __float2half_rn(tile[threadIdx.x][py] * scale);
+  }
+}
+cudaError_t ncthw_to_tokens(cudaStream_t s, const void* x, int is_f32, int B, int C, int T, int HW, __half* y, int ldy,
+                            float scale) {
+  dim3 grid((HW + 31) / 32, (C + 31) / 32, B * T), block(32, 8);
+  if (is_f32) ncthw_to_tokens_kernel<float><<<grid, block, 0, s>>>((const float*)x, B, C, T, HW, y, ldy, scale);
+  else ncthw_to_tokens_kernel<__half><<<grid, block, 0, s>>>((const __half*)x, B, C, T, HW, y, ldy, scale);
+  return cudaGetLastError();
+}
+
+template <typename TOut>
+__global__ void tokens_to_ncthw_kernel(const __half* __restrict__ x, int ldx, int B, int C, int T, int HW,
+                                       TOut* __restrict__ y) {
+  __shared__ float tile[32][33];
+  const int bt = blockIdx.z;
+  const int b = bt / T, t = bt % T;
+  const int p0 = blockIdx.x * 32, c0 = blockIdx.y * 32;
+  for (int py = threadIdx.y; py < 32; py += blockDim.y) {
+    const int p = p0 + py, c = c0 + threadIdx.x;
+    if (c < C && p < HW) tile[py][threadIdx.x] = __half2float(x[((size_t)bt * HW + p) * ldx + c]);
+  }
+  __syncthreads();
+  for (int cy = threadIdx.y; cy < 32; cy += blockDim.y) {
+    const int c = c0 + cy, p = p0 + threadIdx.x;
+    if (c < C && p < HW) y[(((size_t)b * C + c) * T + t) * HW + p] = (TOut)tile[threadIdx.x][cy];
+  }
+}
+cudaError_t tokens_to_ncthw(cudaStream_t s, const __half* x, int ldx, int B, int C, int T, int HW, void* y, int is_f32) {
+  dim3 grid((HW + 31) / 32, (C + 31) / 32, B * T), block(32, 8);
+  if (is_f32) tokens_to_ncthw_kernel<float><<<grid, block, 0, s>>>(x, ldx, B, C, T, HW, (float*)y);
+  else tokens_to_ncthw_kernel<__half><<<grid, block, 0, s>>>(x, ldx, B, C, T, HW, (__half*)y);
+  return cudaGetLastError();
+}
+
+template <typename TIn>
+__global__ void add_nchw_residual_kernel(__half* __restrict__ x, int C, int HW, const TIn* __restrict__ r) {
+  __shared__ float tile[32][33];
+  const int f = blockIdx.z;
+  const int p0 = blockIdx.x * 32, c0 = blockIdx.y * 32;
+  for (int cy = threadIdx.y; cy < 32; cy += blockDim.y) {
+    const int c = c0 + cy, p = p0 + threadIdx.x;
+    if (c < C && p < HW) tile[cy][threadIdx.x] = (float)r[((size_t)f * C + c) * HW + p];
+  }
+  __syncthreads();
+  for (int py = threadIdx.y; py < 32; py += blockDim.y) {
+    const int p = p0 + py, c = c0 + threadIdx.x;
+    if (c < C && p < HW) {
+      __half* d = x + ((size_t)f * HW + p) * C + c;
+      *d = __float2half_rn(__half2float(*d) + tile[threadIdx.x][py]);
+    }
+  }
+}
+cudaError_t add_nchw_residual(cudaStream_t s, __half* x, int NF, int C, int HW, const void* r, int is_f32) {
+  dim3 grid((HW + 31) / 32, (C + 31) / 32, NF), block(32, 8);
+  if (is_f32) add_nchw_residual_kernel<float><<<grid, block, 0, s>>>(x, C, HW, (const float*)r);
+  else add_nchw_residual_kernel<__half><<<grid, block, 0, s>>>(x, C, HW, (const __half*)r);
+  return cudaGetLastError();
+}
+
+// conv_in im2col: one thread per (output pixel, tap); writes Cin values; column = tap*Cin + c; cols >= 9*Cin are zero
+template <typename TIn>
+__global__ void im2col_latent_kernel(const TIn* __restrict__ x, int B, int Cin, int T, int H, int W,
+                                     __half* __restrict__ A) {
+  const long long total = (long long)B * T * H * W;
+  for (long long m = (long long)blockIdx.x * blockDim.x + threadIdx.x; m < total; m += (long long)gridDim.x * blockDim.x) {
+    long long r = m;
+    const int xw = (int)(r % W); r /= W;
+    const int yh = (int)(r % H); r /= H;
+    const int t = (int)(r % T);
+    const int b = (int)(r / T);
+    __align__(16) __half row[64];
+#pragma unroll
+    for (int i = 0; i < 64; ++i) row[i] = __float2half_rn(0.f);
+    for (int tap = 0; tap < 9; ++tap) {
+      const int yy = yh + tap / 3 - 1, xx = xw + tap % 3 - 1;
+      if (yy < 0 || yy >= H || xx < 0 || xx >= W) continue;
+      for (int c = 0; c < Cin; ++c)
+        row[tap * Cin + c] = __float2half_rn((float)x[((((size_t)b * Cin + c) * T + t) * H + yy) * W + xx]);
+    }
+    uint4* dst = reinterpret_cast<uint4*>(A + m * 64);
+#pragma unroll
+    for (int i = 0; i < 8; ++i) dst[i] = reinterpret_cast<const uint4*>(row)[i];
+  }
+}
+cudaError_t im2col_latent(cudaStream_t s, const void* x, int is_f32, int B, int Cin, int T, int H, int W, __half* A) {
+  if (9 * Cin > 64) return cudaErrorInvalidValue;
+  const long long total = (long long)B * T * H * W;
+  const int blocks = (int)((total + 127) / 128);
+  if (is_f32) im2col_latent_kernel<float><<<blocks, 128, 0, s>>>((const float*)x, B, Cin, T, H, W, A);
+  else im2col_latent_kernel<__half><<<blocks, 128, 0, s>>>((const __half*)x, B, Cin, T, H, W, A);
+  return cudaGetLastError();
+}
+
+__global__ void sinusoid_kernel(const float* __restrict__ values, int n, int dim, __half* __restrict__ out, int ld) {
+  const int half_dim = dim / 2;
+  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n * half_dim; i += gridDim.x * blockDim.x) {
+    const int r = i / half_dim, k = i % half_dim;
+    const float freq = expf(-logf(10000.f) * (float)k / (float)half_dim);
+    const float a = values[r] * freq;
+    out[(size_t)r * ld + k] = __float2half_rn(cosf(a));             // flip_sin_to_cos: cos first
+    out[(size_t)r * ld + half_dim + k] = __float2half_rn(sinf(a));
+  }
+}
+cudaError_t sinusoid(cudaStream_t s, const float* values, int n, int dim, __half* out, int ld) {
+  sinusoid_kernel<<<(n * dim / 2 + 255) / 256, 256, 0, s>>>(values, n, dim, out, ld);
+  return cudaGetLastError();
+}
+
+__global__ void expand_rows_kernel(const __half* __restrict__ src, int B, int T, int D, const int* __restrict__ zero_t,
+                                   int nzero, int act, __half* __restrict__ out) {
+  const int total = B * T * D;
+  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < total; i += gridDim.x * blockDim.x) {
+    const int d = i % D;
+    const int bt = i / D;
+    const int b = bt / T, t = bt % T;
+    bool z = false;
+    for (int k = 0; k < nzero; ++k) z |= (zero_t[k] == t);
+    float v = __half2float(src[(size_t)b * D + d]);
+    if (act == 1) v = silu_f(v);
+    out[i] = __float2half_rn(z ? 0.f : v);
+  }
+}
+cudaError_t expand_rows(cudaStream_t s, const __half* src, int B, int T, int D, const int* zero_t, int nzero, int act,
+                        __half* out) {
+  expand_rows_kernel<<<(B * T * D + 255) / 256, 256, 0, s>>>(src, B, T, D, zero_t, nzero, act, out);
+  return cudaGetLastError();
+}
+
+// ------------------------------------------------------------------------------------------------ temporal attention
+// One warp per (batch, pixel, head): T <= 32 query frames, lane i owns query i. K/V rows staged in smem as fp16.
+template <int D8>  // ceil(d / 8)
+__global__ void __launch_bounds__(128)
+temporal_attention_kernel(const __half* __restrict__ qkv, int ld, int B, int T, int HW, int heads, int d, int dp,
+                          float scale, __half* __restrict__ out, int ldo) {
+  extern __shared__ __align__(16) __half sm_ta[];
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int wpb = blockDim.x >> 5;
+  const long long prob = (long long)blockIdx.x * wpb + warp;
+  const long long nprob = (long long)B * HW * heads;
+  if (prob >= nprob) return;
+  const int h = (int)(prob % heads);
+  const long long bp = prob / heads;
+  const int pix = (int)(bp % HW);
+  const int b = (int)(bp / HW);
+  constexpr int DS = D8 * 8;                       // padded row length in smem
+  __half* sq = sm_ta + (size_t)warp * 3 * T * DS;     // q rows [T][DS]
+  __half* sk = sq + T * DS;
+  __half* sv = sk + T * DS;
+  const int hd = heads * dp;
+  // cooperative load: T rows x D8 vectors for q, k, v
+  for (int i = lane; i < T * D8; i += 32) {
+    const int t = i / D8, v8 = i % D8;
+    const __half* row = qkv + (((size_t)b * T + t) * HW + pix) * ld + h * dp + v8 * 8;
+    *reinterpret_cast<uint4*>(sq + t * DS + v8 * 8) = *reinterpret_cast<const uint4*>(row);
+    *reinterpret_cast<uint4*>(sk + t * DS + v8 * 8) = *reinterpret_cast<const uint4*>(row + hd);
+    *reinterpret_cast<uint4*>(sv + t * DS + v8 * 8) = *reinterpret_cast<const uint4*>(row + 2 * hd);
+  }
+  __syncwarp();
+  const int qi = lane < T ? lane : T - 1;
+  float sc[32];
+#pragma unroll
+  for (int j = 0; j < 32; ++j) sc[j] = 0.f;
+  for (int v8 = 0; v8 < D8; ++v8) {
+    const uint4 qv = *reinterpret_cast<const uint4*>(sq + qi * DS + v8 * 8);
+    const __half2* q2 = reinterpret_cast<const __half2*>(&qv);
+    float qf[8];
+#pragma unroll
+    for (int e = 0; e < 4; ++e) { const float2 t2 = __half22float2(q2[e]); qf[2 * e] = t2.x; qf[2 * e + 1] = t2.y; }
+#pragma unroll
+    for (int j = 0; j < 32; ++j) {
+      if (j < T) {
+        const uint4 kv = *reinterpret_cast<const uint4*>(sk + j * DS + v8 * 8);
+        const __half2* k2 = reinterpret_cast<const __half2*>(&kv);
+#pragma unroll
+        for (int e = 0; e < 4; ++e) {
+          const float2 t2 = __half22float2(k2[e]);
+          sc[j] = fmaf(qf[2 * e], t2.x, sc[j]);
+          sc[j] = fmaf(qf[2 * e + 1], t2.y, sc[j]);
+        }
+      }
+    }
+  }
+  float mx = -INFINITY;
+#pragma unroll
+  for (int j = 0; j < 32; ++j) if (j < T) mx = fmaxf(mx, sc[j] * scale);
+  float sum = 0.f;
+#pragma unroll
+  for (int j = 0; j < 32; ++j) {
+    if (j < T) { sc[j] = __expf(sc[j] * scale - mx); sum += sc[j]; }
+  }
+  const float inv = 1.f / sum;
+  for (int v8 = 0; v8 < D8; ++v8) {
+    float o[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+#pragma unroll
+    for (int j = 0; j < 32; ++j) {
+      if (j < T) {
+        const uint4 vv = *reinterpret_cast<const uint4*>(sv + j * DS + v8 * 8);
+        const __half2* v2 = reinterpret_cast<const __half2*>(&vv);
+#pragma unroll
+        for (int e = 0; e < 4; ++e) {
+          const float2 t2 = __half22float2(v2[e]);
+          o[2 * e] = fmaf(sc[j], t2.x, o[2 * e]);
+          o[2 * e + 1] = fmaf(sc[j], t2.y, o[2 * e + 1]);
+        }
+      }
+    }
+    if (lane < T && v8 * 8 < d) {
+      __align__(16) __half oh[8];
+#pragma unroll
+      for (int e = 0; e < 8; ++e) oh[e] = __float2half_rn(o[e] * inv);
+      *reinterpret_cast<uint4*>(out + (((size_t)b * T + lane) * HW + pix) * ldo + h * d + v8 * 8) =
+          *reinterpret_cast<const uint4*>(oh);
+    }
+  }
+}
+
+cudaError_t temporal_attention(cudaStream_t s, const __half* qkv, int ld, int B, int T, int HW, int heads, int d, int dp,
+                               float scale, __half* out, int ldo) {
+  if (T > 32 || (d % 8) || (dp % 8) || dp < d) return cudaErrorInvalidValue;
+  const int D8 = dp / 8;
+  const long long nprob = (long long)B * HW * heads;
+  const int wpb = 4;
+  const unsigned blocks = (unsigned)((nprob + wpb - 1) / wpb);
+  const size_t smem = (size_t)wpb * 3 * T * dp * sizeof(__half);
+#define MVB_TA(N)                                                                                              \
+  case N: {                                                                                                     \
+    static bool set##N = false;                                                                                 \
+    if (!set##N) {                                                                                              \
+      cudaFuncSetAttribute(temporal_attention_kernel<N>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024); \
+      set##N = true;                                                                                            \
+    }                                                                                                           \
+    temporal_attention_kernel<N><<<blocks, wpb * 32, smem, s>>>(qkv, ld, B, T, HW, heads, d, dp, scale, out, ldo); \
+    break;                                                                                                      \
+  }
+  switch (D8) {
+    MVB_TA(1) MVB_TA(2) MVB_TA(4) MVB_TA(6) MVB_TA(10) MVB_TA(20)
+    default: return cudaErrorInvalidValue;
+  }
+#undef MVB_TA
+  return cudaGetLastError();
+}
+
+// ------------------------------------------------------------------------------------------------ step epilogue
+template <typename TLat>
+__global__ void fuse_cfg_ddim_kernel(const float* __restrict__ eps_sum, const float* __restrict__ counter,
+                                     const TLat* __restrict__ lat_in, TLat* __restrict__ lat_out, int B, int C, int T,
+                                     int HW, float g, float a_t, float a_prev, int pred, float clip,
+                                     float* __restrict__ eps_out) {
+  const long long n = (long long)B * C * T * HW;
+  const float sa = sqrtf(a_t), sb = sqrtf(1.f - a_t), sap = sqrtf(a_prev), sbp = sqrtf(1.f - a_prev);
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) {
+    const int t = (int)((i / HW) % T);
+    const float cnt = counter[t];
+    const float u = eps_sum[i] / cnt;                 // uncond half comes first (prompt_embeds = [neg, pos])
+    const float tx = eps_sum[n + i] / cnt;
+    const float e = u + g * (tx - u);
+    const float x = (float)lat_in[i];
+    float x0, eps;
+    if (pred == 0) { x0 = (x - sb * e) / sa; eps = e; }
+    else if (pred == 1) { x0 = sa * x - sb * e; eps = sa * e + sb * x; }      // v_prediction
+    else { x0 = e; eps = (x - sa * x0) / sb; }                                // sample
+    if (clip > 0.f) x0 = fminf(fmaxf(x0, -clip), clip);
+    lat_out[i] = (TLat)(sap * x0 + sbp * eps);
+    if (eps_out) eps_out[i] = e;
+  }
+}
+cudaError_t fuse_cfg_ddim(cudaStream_t s, const float* eps_sum, const float* counter, const void* latents_in,
+                          void* latents_out, int is_f32, int B, int C, int T, int HW, float guidance, float alpha_t,
+                          float alpha_prev, int prediction_type, float clip_range, float* eps_out) {
+  const long long n = (long long)B * C * T * HW;
+  const int blocks = (int)((n + 255) / 256 < 148 * 8 ? (n + 255) / 256 : 148 * 8);
+  if (is_f32)
+    fuse_cfg_ddim_kernel<float><<<blocks, 256, 0, s>>>(eps_sum, counter, (const float*)latents_in, (float*)latents_out,
+                                                       B, C, T, HW, guidance, alpha_t, alpha_prev, prediction_type,
+                                                       clip_range, eps_out);
+  else
+    fuse_cfg_ddim_kernel<__half><<<blocks, 256, 0, s>>>(eps_sum, counter, (const __half*)latents_in,
+                                                        (__half*)latents_out, B, C, T, HW, guidance, alpha_t, alpha_prev,
+                                                        prediction_type, clip_range, eps_out);
+  return cudaGetLastError();
+}
+
+template <typename TIn>
+__global__ void accumulate_window_kernel(float* __restrict__ eps_sum, int B2, int C, int T, int HW,
+                                         const TIn* __restrict__ win, int Tw, int src_t0, const int* __restrict__ frames,
+                                         int nframes) {
+  const long long n = (long long)B2 * C * nframes * HW;
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) {
+    const int p = (int)(i % HW);
+    long long r = i / HW;
+    const int k = (int)(r % nframes); r /= nframes;
+    const int c = (int)(r % C);
+    const int b = (int)(r / C);
+    const float v = (float)win[(((size_t)b * C + c) * Tw + src_t0 + k) * HW + p];
+    eps_sum[(((size_t)b * C + c) * T + frames[k]) * HW + p] += v;
+  }
+}
+cudaError_t accumulate_window(cudaStream_t s, float* eps_sum, int B2, int C, int T, int HW, const void* eps_win,
+                              int is_f32, int Tw, int src_t0, const int* frames_dev, int nframes) {
+  const long long n = (long long)B2 * C * nframes * HW;
+  const int blocks = (int)((n + 255) / 256 < 148 * 8 ? (n + 255) / 256 : 148 * 8);
+  if (is_f32)
+    accumulate_window_kernel<float><<<blocks, 256, 0, s>>>(eps_sum, B2, C, T, HW, (const float*)eps_win, Tw, src_t0,
+                                                           frames_dev, nframes);
+  else
+    accumulate_window_kernel<__half><<<blocks, 256, 0, s>>>(eps_sum, B2, C, T, HW, (const __half*)eps_win, Tw, src_t0,
+                                                            frames_dev, nframes);
+  return cudaGetLastError();
+}
+
+}  // namespace mvb

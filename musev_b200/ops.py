@@ -40,15 +40,17 @@ def conv_gemm(
     geglu: bool = False,
     act: int = 0,
     out: Optional[torch.Tensor] = None,
+    out_f32: bool = False,
+    stride2: bool = False,
 ) -> torch.Tensor:
     assert a0.dtype == torch.float16 and weight.dtype == torch.float16 and a0.dim() == 4
     assert a0.stride(3) == 1 and weight.is_contiguous()
     NF, H, W, C0 = a0.shape
     N = weight.shape[0]
     nout = N // 2 if geglu else N
-    M = NF * H * W
+    M = NF * H * W if not stride2 else NF * (H // 2) * (W // 2)
     if out is None:
-        out = torch.empty((M, nout), dtype=torch.float16, device=a0.device)
+        out = torch.empty((M, nout), dtype=torch.float32 if out_f32 else torch.float16, device=a0.device)
     d = _capi.ConvGemmDesc()
     d.a0, d.c0 = a0.data_ptr(), C0
     d.a0_stride_w, d.a0_stride_h, d.a0_stride_n = a0.stride(2), a0.stride(1), a0.stride(0)
@@ -60,7 +62,7 @@ def conv_gemm(
     d.ntaps = len(taps)
     for i, (dy, dx) in enumerate(taps):
         d.dy[i], d.dx[i] = dy, dx
-    assert weight.shape[1] == len(taps) * (C0 + (a1.shape[3] if a1 is not None else 0))
+    assert stride2 or weight.shape[1] == len(taps) * (C0 + (a1.shape[3] if a1 is not None else 0))
     d.weight, d.N = weight.data_ptr(), N
     d.out, d.ldc = out.data_ptr(), out.stride(0)
     if bias is not None:
@@ -75,5 +77,74 @@ def conv_gemm(
         assert residual.dtype == torch.float16
         d.residual, d.ld_res = residual.data_ptr(), residual.stride(0)
     d.alpha, d.beta, d.geglu, d.act = alpha, beta, int(geglu), act
+    d.out_f32, d.stride2 = int(out_f32), int(stride2)
     _capi.check(_capi.lib().mvb_op_conv_gemm(C.byref(d), _stream()))
     return out
+
+
+def attention(q, segs, NF, Nq, heads, d, dp, scale, out=None, out_scale=1.0, accumulate=False):
+    """q: [NF*Nq, >=heads*dp] fp16 (row stride taken from the tensor); segs: list of dicts
+    {k, v, nk, fdiv, fmul, fadd} with k/v [rows, >=heads*dp] views sharing a row stride."""
+    assert q.dtype == torch.float16 and q.stride(1) == 1
+    if out is None:
+        out = torch.zeros((NF * Nq, heads * d), dtype=torch.float16, device=q.device)
+    a = _capi.AttentionDesc()
+    a.q, a.ldq = q.data_ptr(), q.stride(0)
+    a.NF, a.Nq, a.heads, a.d, a.dp, a.scale, a.nseg = NF, Nq, heads, d, dp, scale, len(segs)
+    for i, s in enumerate(segs):
+        k, v = s["k"], s["v"]
+        assert k.dtype == torch.float16 and v.dtype == torch.float16 and k.stride(0) == v.stride(0)
+        a.k[i], a.v[i], a.ldkv[i], a.kv_rows[i] = k.data_ptr(), v.data_ptr(), k.stride(0), k.shape[0]
+        a.nk[i], a.fdiv[i], a.fmul[i], a.fadd[i] = s["nk"], s.get("fdiv", 1), s.get("fmul", s["nk"]), s.get("fadd", 0)
+    a.out, a.ldo, a.out_scale, a.accumulate = out.data_ptr(), out.stride(0), out_scale, int(accumulate)
+    _capi.check(_capi.lib().mvb_op_attention(C.byref(a), _stream()))
+    return out
+
+
+def temporal_attention(qkv, B, T, HW, heads, d, dp, scale):
+    assert qkv.dtype == torch.float16 and qkv.is_contiguous()
+    out = torch.empty((B * T * HW, heads * d), dtype=torch.float16, device=qkv.device)
+    _capi.check(_capi.lib().mvb_op_temporal_attention(qkv.data_ptr(), qkv.shape[-1], B, T, HW, heads, d, dp, scale,
+                                                      out.data_ptr(), out.shape[-1], _stream()))
+    return out
+
+
+def groupnorm(x0, gamma, beta, groups=32, frames_per_stat=1, eps=1e-5, silu=False, x1=None):
+    """x0 [NF, HW, C0] fp16 (+ x1 [NF, HW, C1]); gamma/beta fp32 [C0+C1]."""
+    NF, HW, C0 = x0.shape
+    C1 = 0 if x1 is None else x1.shape[2]
+    y = torch.empty((NF, HW, C0 + C1), dtype=torch.float16, device=x0.device)
+    scratch = torch.empty(NF * 16 * groups * 2, dtype=torch.float32, device=x0.device)
+    _capi.check(_capi.lib().mvb_op_groupnorm(x0.data_ptr(), C0, _ptr(x1), C1, NF, HW, groups, frames_per_stat, eps,
+                                             gamma.data_ptr(), beta.data_ptr(), int(silu), y.data_ptr(),
+                                             scratch.data_ptr(), _stream()))
+    return y
+
+
+def layernorm(x, gamma, beta, eps):
+    M, Cc = x.shape
+    y = torch.empty_like(x)
+    _capi.check(_capi.lib().mvb_op_layernorm(x.data_ptr(), M, Cc, eps, gamma.data_ptr(), beta.data_ptr(), y.data_ptr(),
+                                             _stream()))
+    return y
+
+
+def fuse_cfg_ddim(eps_sum, counter, latents, guidance, alpha_t, alpha_prev, prediction_type=0, clip_range=0.0,
+                  out=None, eps_out=None):
+    """eps_sum fp32 [2B,C,T,H,W]; counter fp32 [T]; latents fp32/fp16 [B,C,T,H,W]."""
+    B, Cc, T = latents.shape[:3]
+    HW = latents.shape[3] * latents.shape[4]
+    if out is None:
+        out = torch.empty_like(latents)
+    _capi.check(_capi.lib().mvb_fuse_cfg_ddim(eps_sum.data_ptr(), counter.data_ptr(), latents.data_ptr(), out.data_ptr(),
+                                              int(latents.dtype == torch.float32), B, Cc, T, HW, guidance, alpha_t,
+                                              alpha_prev, prediction_type, clip_range, _ptr(eps_out), _stream()))
+    return out
+
+
+def accumulate_window(eps_sum, eps_win, src_t0, frames_dev):
+    B2, Cc, T = eps_sum.shape[:3]
+    HW = eps_sum.shape[3] * eps_sum.shape[4]
+    _capi.check(_capi.lib().mvb_accumulate_window(eps_sum.data_ptr(), B2, Cc, T, HW, eps_win.data_ptr(),
+                                                  int(eps_win.dtype == torch.float32), eps_win.shape[2], src_t0,
+                                                  frames_dev.data_ptr(), frames_dev.numel(), _stream()))

@@ -1,0 +1,175 @@
+"""TEST INFRASTRUCTURE ONLY -- generates tests/golden/* by running the UNMODIFIED reference (/root/reference) on CPU.
+
+Run in the build container only:  python -m oracle.make_golden [--full]
+The fixtures hold seeds + reference outputs; weights and inputs are regenerated from the seeds by
+musev_b200.synth (bit-identical CPU RNG), so the files stay small. /root/reference is never read at test time.
+"""
+from __future__ import annotations
+
+import argparse
+import importlib.util
+import json
+import os
+import sys
+import time
+
+import torch
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+from musev_b200.schema import preset_config, unet_param_shapes  # noqa: E402
+from musev_b200.synth import make_inputs, make_state_dict  # noqa: E402
+from oracle import ref_shim  # noqa: E402
+from oracle.pipeline_oracle import SD15_DDIM  # noqa: E402
+
+GOLDEN = os.path.join(ROOT, "tests", "golden")
+NARROW = (64, 128, 128, 128)
+FULL = (320, 640, 1280, 1280)
+
+
+def build_reference(preset: str, boc, sd):
+    U, _ = ref_shim.load()
+    kw = dict(ref_shim.SD15_KW)
+    kw.update(ref_shim.PRESET_KW[preset])
+    kw["block_out_channels"] = boc
+    cfg = preset_config(preset, block_out_channels=boc)
+    with torch.device("meta"):
+        m = U(**kw)
+    ref_shapes = {k: tuple(v.shape) for k, v in m.state_dict().items()}
+    mine = {k: tuple(v) for k, v in unet_param_shapes(cfg).items()}
+    assert ref_shapes == mine, "schema mismatch vs reference state_dict"
+    m = m.to_empty(device="cpu")
+    missing = m.load_state_dict(sd, strict=True)
+    assert not missing.missing_keys and not missing.unexpected_keys
+    return m.eval(), cfg
+
+
+def run_reference_unet(m, inp, t, frame_rate, ip_scale):
+    with torch.no_grad():
+        return m(inp["sample"], torch.tensor(t), inp["encoder_hidden_states"], sample_index=inp["sample_index"],
+                 vision_conditon_frames_sample_index=inp["vision_conditon_frames_sample_index"],
+                 sample_frame_rate=frame_rate, do_classifier_free_guidance=True,
+                 down_block_refer_embs=inp.get("down_block_refer_embs"),
+                 mid_block_refer_emb=inp.get("mid_block_refer_emb"), vision_clip_emb=inp.get("vision_clip_emb"),
+                 ip_adapter_scale=ip_scale)[0]
+
+
+def golden_unet(preset, boc, tag, batch, frames, h, w, t, wseed=0, iseed=1234, frame_rate=8, ip_scale=0.7):
+    cfg = preset_config(preset, block_out_channels=boc)
+    t0 = time.time()
+    sd = make_state_dict(cfg, seed=wseed)
+    m, cfg = build_reference(preset, boc, sd)
+    inp = make_inputs(cfg, batch=batch, frames=frames, h=h, w=w, n_vis_cond=1, seed=iseed)
+    out = run_reference_unet(m, inp, t, frame_rate, ip_scale)
+    meta = dict(preset=preset, block_out_channels=list(boc), batch=batch, frames=frames, h=h, w=w, timestep=t,
+                weight_seed=wseed, input_seed=iseed, sample_frame_rate=frame_rate, ip_adapter_scale=ip_scale,
+                n_vis_cond=1, source="reference musev.models.unet_3d_condition.UNet3DConditionModel, CPU fp32")
+    path = os.path.join(GOLDEN, f"unet_{preset}_{tag}.pt")
+    torch.save({"meta": meta, "out": out.clone()}, path)
+    print(f"{path}: out std {out.std().item():.4f} ({time.time() - t0:.1f}s)", flush=True)
+    return m, cfg, sd
+
+
+def golden_loop(preset, boc, tag, m, cfg, T=20, h=8, w=8, steps=2, wseed=0, iseed=77):
+    """Restates the window loop (pipeline_controlnet.py:1846-2117) around the IMPORTED UNet and the IMPORTED
+    musev DDIMScheduler + prepare_global_context."""
+    _, DDIM = ref_shim.load()
+    spec = importlib.util.spec_from_file_location(
+        "mmcm.utils.itertools_util", os.path.join(ref_shim.REFERENCE_ROOT, "MMCM/mmcm/utils/itertools_util.py"))
+    mod = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(mod)
+    sys.modules["mmcm.utils.itertools_util"] = mod
+    from musev.pipelines.context import prepare_global_context
+
+    sched = DDIM(**SD15_DDIM)
+    sched.set_timesteps(steps)
+    g = torch.Generator().manual_seed(iseed)
+    latents = torch.randn(1, 4, T, h, w, generator=g)
+    cond = torch.randn(1, 4, 1, h, w, generator=g) * 0.5
+    prompt = torch.randn(2, 77, cfg.cross_attention_dim, generator=g)
+    extra = make_inputs(cfg, batch=2, frames=1, h=h, w=w, seed=iseed)
+    kw = {k: extra[k] for k in ("down_block_refer_embs", "mid_block_refer_emb", "vision_clip_emb") if k in extra}
+    ctx = prepare_global_context("uniform_v2", steps, T, 8, 1, 2, 1)
+    gs = 3.5
+    vis_idx = torch.arange(1)
+    with torch.no_grad():
+        for t in sched.timesteps:
+            noise_pred = torch.zeros(2, 4, T, h, w)
+            counter = torch.zeros(1, 1, T, 1, 1)
+            for context in ctx:
+                c = context[0]
+                lat = torch.cat([latents[:, :, c]] * 2)
+                sub = torch.arange(len(c)) + 1
+                full = torch.zeros(2, 4, 1 + len(c), h, w)
+                full[:, :, vis_idx] = torch.cat([cond] * 2)
+                full[:, :, sub] = lat
+                eps = m(full, t, prompt, sample_index=sub, vision_conditon_frames_sample_index=vis_idx,
+                        sample_frame_rate=8, do_classifier_free_guidance=True, ip_adapter_scale=1.0, **kw)[0]
+                noise_pred[:, :, c] += eps[:, :, sub]
+                counter[:, :, c] += 1
+            noise_pred = noise_pred / counter
+            u, tx = noise_pred.chunk(2)
+            noise_pred = u + gs * (tx - u)
+            latents_next = sched.step(noise_pred, t, latents, eta=0.0).prev_sample
+            latents = latents_next
+    meta = dict(preset=preset, block_out_channels=list(boc), T=T, h=h, w=w, steps=steps, weight_seed=wseed,
+                input_seed=iseed, context_frames=8, context_overlap=2, guidance_scale=gs, contexts=[c[0] for c in ctx],
+                source="imported reference UNet + musev DDIMScheduler + prepare_global_context; loop restated")
+    path = os.path.join(GOLDEN, f"loop_{preset}_{tag}.pt")
+    torch.save({"meta": meta, "latents": latents.clone()}, path)
+    print(path, "final latents std", latents.std().item(), flush=True)
+
+
+def golden_contexts():
+    spec = importlib.util.spec_from_file_location(
+        "mmcm.utils.itertools_util", os.path.join(ref_shim.REFERENCE_ROOT, "MMCM/mmcm/utils/itertools_util.py"))
+    mod = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(mod)
+    sys.modules["mmcm.utils.itertools_util"] = mod
+    ref_shim.load()
+    from musev.pipelines.context import prepare_global_context
+
+    cases = []
+    for sched in ("uniform", "uniform_v2"):
+        for (T, win, ov) in [(16, 16, 4), (48, 16, 4), (48, 16, 8), (128, 16, 4), (512, 16, 8), (12, 12, 4),
+                             (20, 8, 2), (7, 12, 4), (33, 12, 4)]:
+            ctx = prepare_global_context(sched, 20, T, win, 1, ov, 1)
+            cases.append(dict(schedule=sched, T=T, window=win, overlap=ov,
+                              contexts=[[int(i) for i in c[0]] for c in ctx]))
+    with open(os.path.join(GOLDEN, "contexts.json"), "w") as fh:
+        json.dump(cases, fh)
+    print("contexts.json", len(cases), "cases")
+
+
+def golden_ddim():
+    _, DDIM = ref_shim.load()
+    sched = DDIM(**SD15_DDIM)
+    sched.set_timesteps(20)
+    g = torch.Generator().manual_seed(5)
+    x = torch.randn(1, 4, 3, 8, 8, generator=g)
+    eps = torch.randn(1, 4, 3, 8, 8, generator=g)
+    outs = {}
+    for t in (951, 501, 1):
+        outs[str(t)] = sched.step(eps, t, x, eta=0.0).prev_sample.clone()
+    torch.save({"timesteps": sched.timesteps.clone(), "x": x, "eps": eps, "prev": outs,
+                "source": "musev.schedulers.DDIMScheduler (imported reference), SD-1.5 config, 20 steps"},
+               os.path.join(GOLDEN, "ddim_sd15.pt"))
+    print("ddim_sd15.pt timesteps", sched.timesteps.tolist())
+
+
+if __name__ == "__main__":
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--full", action="store_true", help="also produce the full-width (1.4 B parameter) fixtures")
+    args = ap.parse_args()
+    os.makedirs(GOLDEN, exist_ok=True)
+    torch.set_num_threads(os.cpu_count() or 1)
+    golden_contexts()
+    golden_ddim()
+    for preset in ("musev", "musev_referencenet"):
+        m, cfg, sd = golden_unet(preset, NARROW, "narrow", batch=2, frames=4, h=16, w=16, t=601)
+        golden_loop(preset, NARROW, "narrow", m, cfg)
+        del m, sd
+    if args.full:
+        for preset in ("musev", "musev_referencenet"):
+            m, cfg, sd = golden_unet(preset, FULL, "full", batch=2, frames=2, h=8, w=8, t=601)
+            del m, sd
