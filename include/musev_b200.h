@@ -101,13 +101,17 @@ int mvb_op_groupnorm(const void* x0, int c0, const void* x1, int c1, int NF, int
 int mvb_op_layernorm(const void* x, long long M, int C, float eps, const float* gamma, const float* beta, void* y,
                      void* stream);
 
-/* Fused overlap mean + classifier-free guidance + DDIM step, eta = 0
- * (musev/pipelines/pipeline_controlnet.py:2079,2101-2117; musev/schedulers/scheduling_ddim.py:198-264).
- * eps_sum fp32 [2B,C,T,HW] (uncond half first), counter fp32 [T], latents fp32 (is_f32) or fp16 [B,C,T,HW].
- * prediction_type: 0 epsilon, 1 v_prediction, 2 sample. clip_range <= 0 disables clipping. eps_out may be NULL. */
+/* Fused overlap mean + classifier-free guidance + DDIM step
+ * (musev/pipelines/pipeline_controlnet.py:2079,2101-2117; musev/schedulers/scheduling_ddim.py:198-295).
+ *   eps = eps_sum / counter[t];  cfg: eps = uncond + g * (text - uncond)   (eps_sum fp32 [2B,C,T,HW], uncond first)
+ *   x0 from eps / v / sample prediction (prediction_type 0 / 1 / 2), optional clip to +-clip_range (<= 0: off),
+ *   x_prev = sqrt(a_prev) x0 + sqrt(1 - a_prev - std^2) eps (+ std * variance_noise when eta > 0).
+ * cfg = 0: eps_sum is a single [B,C,T,HW] prediction -- this is plain `DDIMScheduler.step`. counter, variance_noise,
+ * eps_out, x0_out may be NULL. latents fp32 (is_f32) or fp16 [B,C,T,HW]. */
 int mvb_fuse_cfg_ddim(const float* eps_sum, const float* counter, const void* latents_in, void* latents_out,
-                      int is_f32, int B, int C, int T, int HW, float guidance_scale, float alpha_prod_t,
-                      float alpha_prod_t_prev, int prediction_type, float clip_range, float* eps_out, void* stream);
+                      int is_f32, int B, int C, int T, int HW, int cfg, float guidance_scale, float alpha_prod_t,
+                      float alpha_prod_t_prev, int prediction_type, float clip_range, int use_clipped_model_output,
+                      float std_dev_t, const float* variance_noise, float* eps_out, float* x0_out, void* stream);
 
 /* eps_sum[:, :, frames[i]] += eps_window[:, :, src_t0 + i] (musev/pipelines/pipeline_controlnet.py:2068-2078).
  * eps_window [2B, C, Tw, HW] fp32/fp16; frames_dev: device int32[nframes]. */

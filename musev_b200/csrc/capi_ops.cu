@@ -101,11 +101,15 @@ int mvb_op_layernorm(const void* x, long long M, int C, float eps, const float* 
 }
 
 int mvb_fuse_cfg_ddim(const float* eps_sum, const float* counter, const void* latents_in, void* latents_out,
-                      int is_f32, int B, int C, int T, int HW, float guidance_scale, float alpha_prod_t,
-                      float alpha_prod_t_prev, int prediction_type, float clip_range, float* eps_out, void* stream) {
-  if (!eps_sum || !counter || !latents_in || !latents_out) return fail("mvb_fuse_cfg_ddim: null pointer", cudaSuccess);
-  cudaError_t e = fuse_cfg_ddim((cudaStream_t)stream, eps_sum, counter, latents_in, latents_out, is_f32, B, C, T, HW,
-                                guidance_scale, alpha_prod_t, alpha_prod_t_prev, prediction_type, clip_range, eps_out);
+                      int is_f32, int B, int C, int T, int HW, int cfg, float guidance_scale, float alpha_prod_t,
+                      float alpha_prod_t_prev, int prediction_type, float clip_range, int use_clipped_model_output,
+                      float std_dev_t, const float* variance_noise, float* eps_out, float* x0_out, void* stream) {
+  if (!eps_sum || !latents_in || !latents_out) return fail("mvb_fuse_cfg_ddim: null pointer", cudaSuccess);
+  if (alpha_prod_t <= 0.f || alpha_prod_t > 1.f || prediction_type < 0 || prediction_type > 2)
+    return fail("mvb_fuse_cfg_ddim: bad alpha / prediction_type", cudaSuccess);
+  cudaError_t e = fuse_cfg_ddim((cudaStream_t)stream, eps_sum, counter, latents_in, latents_out, is_f32, B, C, T, HW, cfg,
+                                guidance_scale, alpha_prod_t, alpha_prod_t_prev, prediction_type, clip_range,
+                                use_clipped_model_output, std_dev_t, variance_noise, eps_out, x0_out);
   if (e != cudaSuccess) return fail("mvb_fuse_cfg_ddim", e);
   return MVB_OK;
 }

@@ -528,39 +528,49 @@ cudaError_t temporal_attention(cudaStream_t s, const __half* qkv, int ld, int B,
 template <typename TLat>
 __global__ void fuse_cfg_ddim_kernel(const float* __restrict__ eps_sum, const float* __restrict__ counter,
                                      const TLat* __restrict__ lat_in, TLat* __restrict__ lat_out, int B, int C, int T,
-                                     int HW, float g, float a_t, float a_prev, int pred, float clip,
-                                     float* __restrict__ eps_out) {
+                                     int HW, int cfg, float g, float a_t, float a_prev, int pred, float clip,
+                                     int use_clipped, float std_dev, const float* __restrict__ noise,
+                                     float* __restrict__ eps_out, float* __restrict__ x0_out) {
   const long long n = (long long)B * C * T * HW;
-  const float sa = sqrtf(a_t), sb = sqrtf(1.f - a_t), sap = sqrtf(a_prev), sbp = sqrtf(1.f - a_prev);
+  const float sa = sqrtf(a_t), sb = sqrtf(1.f - a_t), sap = sqrtf(a_prev);
+  const float sdir = sqrtf(fmaxf(1.f - a_prev - std_dev * std_dev, 0.f));
   for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) {
     const int t = (int)((i / HW) % T);
-    const float cnt = counter[t];
-    const float u = eps_sum[i] / cnt;                 // uncond half comes first (prompt_embeds = [neg, pos])
-    const float tx = eps_sum[n + i] / cnt;
-    const float e = u + g * (tx - u);
+    const float cnt = counter ? counter[t] : 1.f;
+    float e = eps_sum[i] / cnt;                       // uncond half comes first (prompt_embeds = [neg, pos])
+    if (cfg) {
+      const float tx = eps_sum[n + i] / cnt;
+      e = e + g * (tx - e);
+    }
     const float x = (float)lat_in[i];
     float x0, eps;
     if (pred == 0) { x0 = (x - sb * e) / sa; eps = e; }
     else if (pred == 1) { x0 = sa * x - sb * e; eps = sa * e + sb * x; }      // v_prediction
     else { x0 = e; eps = (x - sa * x0) / sb; }                                // sample
     if (clip > 0.f) x0 = fminf(fmaxf(x0, -clip), clip);
-    lat_out[i] = (TLat)(sap * x0 + sbp * eps);
+    if (use_clipped) eps = (x - sa * x0) / sb;
+    float prev = sap * x0 + sdir * eps;
+    if (noise) prev += std_dev * noise[i];
+    lat_out[i] = (TLat)prev;
     if (eps_out) eps_out[i] = e;
+    if (x0_out) x0_out[i] = x0;
   }
 }
 cudaError_t fuse_cfg_ddim(cudaStream_t s, const float* eps_sum, const float* counter, const void* latents_in,
-                          void* latents_out, int is_f32, int B, int C, int T, int HW, float guidance, float alpha_t,
-                          float alpha_prev, int prediction_type, float clip_range, float* eps_out) {
+                          void* latents_out, int is_f32, int B, int C, int T, int HW, int cfg, float guidance,
+                          float alpha_t, float alpha_prev, int prediction_type, float clip_range, int use_clipped,
+                          float std_dev, const float* noise, float* eps_out, float* x0_out) {
   const long long n = (long long)B * C * T * HW;
   const int blocks = (int)((n + 255) / 256 < 148 * 8 ? (n + 255) / 256 : 148 * 8);
   if (is_f32)
     fuse_cfg_ddim_kernel<float><<<blocks, 256, 0, s>>>(eps_sum, counter, (const float*)latents_in, (float*)latents_out,
-                                                       B, C, T, HW, guidance, alpha_t, alpha_prev, prediction_type,
-                                                       clip_range, eps_out);
+                                                       B, C, T, HW, cfg, guidance, alpha_t, alpha_prev, prediction_type,
+                                                       clip_range, use_clipped, std_dev, noise, eps_out, x0_out);
   else
     fuse_cfg_ddim_kernel<__half><<<blocks, 256, 0, s>>>(eps_sum, counter, (const __half*)latents_in,
-                                                        (__half*)latents_out, B, C, T, HW, guidance, alpha_t, alpha_prev,
-                                                        prediction_type, clip_range, eps_out);
+                                                        (__half*)latents_out, B, C, T, HW, cfg, guidance, alpha_t,
+                                                        alpha_prev, prediction_type, clip_range, use_clipped, std_dev,
+                                                        noise, eps_out, x0_out);
   return cudaGetLastError();
 }
 

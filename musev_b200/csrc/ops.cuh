@@ -47,11 +47,13 @@ cudaError_t temporal_attention(cudaStream_t s, const __half* qkv, int ld, int B,
 // Fused overlap mean + classifier-free guidance + DDIM update (pipeline_controlnet.py:2079,2101-2117;
 // scheduling_ddim.py:198-264 with eta = 0):
 //   eps = eps_sum / counter[t]; eps = uncond + g * (text - uncond); x0 = (x - sqrt(1-a_t) eps) / sqrt(a_t) [clip];
-//   x_prev = sqrt(a_prev) x0 + sqrt(1 - a_prev) eps_used
+//   x_prev = sqrt(a_prev) x0 + sqrt(1 - a_prev - std^2) eps_used (+ std * noise when eta > 0)
+// cfg = 0: eps_sum holds a single [B,...] prediction (plain scheduler.step); counter may be null (= 1).
 // eps_sum fp32 [2B,C,T,HW] (uncond first), latents fp32 or fp16 [B,C,T,HW].
 cudaError_t fuse_cfg_ddim(cudaStream_t s, const float* eps_sum, const float* counter, const void* latents_in,
-                          void* latents_out, int is_f32, int B, int C, int T, int HW, float guidance, float alpha_t,
-                          float alpha_prev, int prediction_type, float clip_range, float* eps_out);
+                          void* latents_out, int is_f32, int B, int C, int T, int HW, int cfg, float guidance,
+                          float alpha_t, float alpha_prev, int prediction_type, float clip_range, int use_clipped,
+                          float std_dev, const float* noise, float* eps_out, float* x0_out);
 // eps_sum[:, :, frames[i]] += eps_window[:, :, src_t0 + i]   (pipeline_controlnet.py:2068-2078)
 cudaError_t accumulate_window(cudaStream_t s, float* eps_sum, int B2, int C, int T, int HW, const void* eps_win,
                               int is_f32, int Tw, int src_t0, const int* frames_dev, int nframes);

@@ -130,15 +130,17 @@ def layernorm(x, gamma, beta, eps):
 
 
 def fuse_cfg_ddim(eps_sum, counter, latents, guidance, alpha_t, alpha_prev, prediction_type=0, clip_range=0.0,
-                  out=None, eps_out=None):
-    """eps_sum fp32 [2B,C,T,H,W]; counter fp32 [T]; latents fp32/fp16 [B,C,T,H,W]."""
+                  out=None, eps_out=None, cfg=True, use_clipped=False, std_dev=0.0, noise=None, x0_out=None):
+    """eps_sum fp32 [2B,C,T,H,W] (cfg) or [B,C,T,H,W]; counter fp32 [T] or None; latents fp32/fp16 [B,C,T,H,W]."""
     B, Cc, T = latents.shape[:3]
     HW = latents.shape[3] * latents.shape[4]
+    assert eps_sum.dtype == torch.float32 and eps_sum.is_contiguous() and latents.is_contiguous()
     if out is None:
         out = torch.empty_like(latents)
-    _capi.check(_capi.lib().mvb_fuse_cfg_ddim(eps_sum.data_ptr(), counter.data_ptr(), latents.data_ptr(), out.data_ptr(),
-                                              int(latents.dtype == torch.float32), B, Cc, T, HW, guidance, alpha_t,
-                                              alpha_prev, prediction_type, clip_range, _ptr(eps_out), _stream()))
+    _capi.check(_capi.lib().mvb_fuse_cfg_ddim(
+        eps_sum.data_ptr(), _ptr(counter), latents.data_ptr(), out.data_ptr(), int(latents.dtype == torch.float32),
+        B, Cc, T, HW, int(cfg), guidance, alpha_t, alpha_prev, prediction_type, clip_range, int(use_clipped),
+        std_dev, _ptr(noise), _ptr(eps_out), _ptr(x0_out), _stream()))
     return out
 
 

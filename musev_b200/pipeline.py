@@ -1,0 +1,115 @@
+"""Visual-Conditioned Parallel-Denoise loop on the B200 engine.
+
+Mirrors the loop body of `MusevControlNetPipeline.__call__` (musev/pipelines/pipeline_controlnet.py:1846-2147):
+per step, every window -> UNet -> accumulate eps; overlap mean; CFG; scheduler.step. What changes:
+  * the UNet forward is the CUDA engine (musev_b200.unet.UNet3DConditionModel);
+  * the ~12 pointwise launches of mean / CFG / DDIM are ONE kernel (`mvb_fuse_cfg_ddim`);
+  * windows are sharded over the ranks of a torch.distributed process group (one process per GPU) with exactly one
+    all-reduce (sum) of the eps accumulator per step -- the reference loops over windows on a single GPU. Every
+    rank keeps the full latents and applies the identical fused update, so latents stay replicated bit-exactly.
+"""
+from __future__ import annotations
+
+from dataclasses import dataclass
+from typing import Callable, Dict, List, Optional, Sequence
+
+import torch
+
+from . import ops
+from .context import assign_windows, prepare_global_context
+from .scheduler import DDIMScheduler, _PRED
+
+
+@dataclass
+class DenoiseOutput:
+    latents: torch.Tensor
+    windows: List[List[int]]
+    windows_per_rank: List[List[int]]
+
+
+class ParallelDenoiser:
+    def __init__(self, unet, scheduler: DDIMScheduler, process_group=None, device_ops=None):
+        # device_ops: module providing accumulate_window / fuse_cfg_ddim; the CUDA library unless a test injects a double
+        self.ops = device_ops if device_ops is not None else ops
+        self.unet = unet
+        self.scheduler = scheduler
+        self.pg = process_group
+        self._dist = None
+        if process_group is not None or (torch.distributed.is_available() and torch.distributed.is_initialized()):
+            import torch.distributed as dist
+            self._dist = dist
+        self.rank = self._dist.get_rank(self.pg) if self._dist else 0
+        self.world = self._dist.get_world_size(self.pg) if self._dist else 1
+
+    @torch.no_grad()
+    def __call__(
+        self,
+        latents: torch.Tensor,                 # [B, 4, T, h, w] initial noise * init_noise_sigma
+        condition_latents: torch.Tensor,       # [B, 4, n_vc, h, w] vision-condition latents
+        prompt_embeds: torch.Tensor,           # [2B, 77, 768] = cat([negative, positive]) (pipeline_controlnet.py:1565-1577)
+        num_inference_steps: int = 20,
+        guidance_scale: float = 3.5,
+        context_frames: int = 12,
+        context_overlap: int = 4,
+        context_schedule: str = "uniform_v2",
+        context_stride: int = 1,
+        motion_speed: float = 8.0,
+        eta: float = 0.0,
+        unet_kwargs: Optional[dict] = None,    # down_block_refer_embs / mid_block_refer_emb / vision_clip_emb / ip_adapter_scale
+        controlnet_fn: Optional[Callable] = None,  # (window frame list, latent_model_input, t) -> (down_res, mid_res)
+        callback: Optional[Callable] = None,
+        guidance_scale_lst: Optional[Sequence[float]] = None,
+    ) -> DenoiseOutput:
+        if guidance_scale <= 1.0:
+            # the reference's CFG-off branch feeds the wrong vis-cond tensor (pipeline_controlnet.py:1922-1926, Q14)
+            raise NotImplementedError("parallel denoise is implemented for classifier-free guidance (guidance_scale > 1)")
+        if eta != 0.0:
+            raise NotImplementedError("the fused step implements eta = 0 (the pipeline default); use scheduler.step for eta > 0")
+        unet_kwargs = dict(unet_kwargs or {})
+        dev = latents.device
+        B, C, T, h, w = latents.shape
+        n_vc = condition_latents.shape[2]
+        sch = self.scheduler
+        sch.set_timesteps(num_inference_steps, device="cpu")
+        contexts = [c[0] for c in prepare_global_context(context_schedule, num_inference_steps, T, context_frames,
+                                                         context_stride, context_overlap, 1)]
+        per_rank = assign_windows([len(c) for c in contexts], self.world)
+        mine = per_rank[self.rank]
+        counter = torch.zeros(T, dtype=torch.float32)
+        for c in contexts:
+            for fidx in c:
+                counter[fidx] += 1                                                  # :2077, static per call
+        counter = counter.to(dev)
+        frame_idx_dev = [torch.tensor(c, dtype=torch.int32, device=dev) for c in contexts]
+        frame_idx_long = [torch.tensor(c, dtype=torch.long, device=dev) for c in contexts]
+        cond2 = torch.cat([condition_latents] * 2).to(latents.dtype)                # :1921-1926
+        vis_idx = torch.arange(n_vc)
+        eps_sum = torch.zeros((2 * B, C, T, h, w), dtype=torch.float32, device=dev)
+        latents = latents.contiguous()
+        pred = _PRED[sch.config.prediction_type]
+        clip = sch.config.clip_sample_range if sch.config.clip_sample else 0.0
+        for i, t in enumerate(sch.timesteps.tolist()):
+            eps_sum.zero_()                                                         # :1870-1876
+            for wi in mine:                                                         # :1900 (this rank's windows)
+                c = contexts[wi]
+                lat_c = latents.index_select(2, frame_idx_long[wi])                 # :1902
+                sub_idx = torch.arange(len(c)) + n_vc                               # :1914-1920
+                # batch_concat_two_tensor_with_index: vis-cond frames first, then the window, duplicated for CFG
+                model_in = torch.cat([cond2, torch.cat([lat_c] * 2)], dim=2)        # :1908-1946
+                kw = dict(unet_kwargs)
+                if controlnet_fn is not None:
+                    down_res, mid_res = controlnet_fn(c, model_in, t)               # :2022-2038
+                    kw["down_block_additional_residuals"] = down_res
+                    kw["mid_block_additional_residual"] = mid_res
+                eps = self.unet(model_in, t, prompt_embeds, sample_index=sub_idx,
+                                vision_conditon_frames_sample_index=vis_idx, sample_frame_rate=motion_speed,
+                                do_classifier_free_guidance=True, return_dict=False, **kw)[0]   # :2045-2067
+                self.ops.accumulate_window(eps_sum, eps, n_vc, frame_idx_dev[wi])        # :2068-2078
+            if self.world > 1:
+                self._dist.all_reduce(eps_sum, op=self._dist.ReduceOp.SUM, group=self.pg)
+            a_t, a_p, _ = sch.step_scalars(t, 0.0)
+            g = guidance_scale_lst[i] if guidance_scale_lst is not None else guidance_scale
+            latents = self.ops.fuse_cfg_ddim(eps_sum, counter, latents, float(g), a_t, a_p, pred, clip)  # :2079,2101-2117
+            if callback is not None:
+                callback(i, t, latents)
+        return DenoiseOutput(latents=latents, windows=contexts, windows_per_rank=per_rank)
