@@ -1,0 +1,274 @@
+#!/usr/bin/env python
+"""Headline benchmark: denoised frames/s at 512x512, 16-frame window, 20 DDIM steps (BASELINE.json, config 2).
+
+  python bench.py [--gpus N] [--steps K] [--warmup W] [--impl reference]
+  (N > 1: python -m torch.distributed.run --nnodes=1 --nproc-per-node N --master-addr 127.0.0.1 ... bench.py --gpus N ...)
+
+One "step" = one complete denoise of the workload: 20 DDIM steps of the Visual-Conditioned Parallel-Denoise loop
+(every window: UNet3D forward with CFG batch 2 -> overlap mean -> CFG -> DDIM update) on synthetic latents.
+N = 1: config 2 of BASELINE.json (one 16-frame window + 1 vision-condition frame, 64x64 latents, `musev` preset).
+N > 1: weak scaling -- one 16-frame window per GPU (video length 16 + 12 (N-1), window 16, overlap 4), windows sharded
+over the ranks, one NCCL all-reduce of the eps accumulator per DDIM step.
+Prints ONE JSON line on rank 0 (contract in the task statement; extra keys: roofline, cpu_baseline, e2e, clocks).
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import statistics
+import subprocess
+import sys
+import threading
+import time
+
+import torch
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+DDIM_STEPS = 20
+WINDOW, OVERLAP = 16, 4
+LAT_H = LAT_W = 64
+GUIDANCE = 3.5
+PRESET = "musev"
+METRIC = "denoised frames/sec at 512x512, 16-frame window, 20 DDIM steps"
+
+
+def parse():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=3)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="musev_b200", choices=["musev_b200", "reference"])
+    ap.add_argument("--preset", default=PRESET)
+    ap.add_argument("--skip-cpu-baseline", action="store_true")
+    return ap.parse_args()
+
+
+def video_frames(n_gpus: int) -> int:
+    return WINDOW + (WINDOW - OVERLAP) * (n_gpus - 1)
+
+
+class ClockSampler(threading.Thread):
+    """nvidia-smi clocks / throttle reasons sampled DURING the timed region."""
+
+    Q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+         "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index: int):
+        super().__init__(daemon=True)
+        self.index, self.samples, self.stop_flag = index, [], False
+
+    def run(self):
+        while not self.stop_flag:
+            try:
+                out = subprocess.run(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-i",
+                                      str(self.index)], capture_output=True, text=True, timeout=5).stdout.strip()
+                if out:
+                    self.samples.append([x.strip() for x in out.split(",")])
+            except Exception:
+                pass
+            time.sleep(0.2)
+
+    def summary(self):
+        sm = [float(s[0]) for s in self.samples if s and s[0].replace(".", "").isdigit()]
+        mx = [float(s[1]) for s in self.samples if len(s) > 1 and s[1].replace(".", "").isdigit()]
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        reasons = [n for i, n in enumerate(names) if any(len(s) > 3 + i and s[3 + i].lower().startswith("active") for s in self.samples)]
+        return {"sm_mhz": statistics.median(sm) if sm else None, "sm_max_mhz": max(mx) if mx else None,
+                "reasons": reasons, "samples": len(self.samples)}
+
+
+def cpu_baseline(preset: str, frames: int = 4, threads: int | None = None):
+    """The oracle (CPU restatement of the reference, oracle/unet3d_oracle.py) timed on the host cores on a bounded
+    sample: ONE window-step (UNet forward, CFG batch 2) of `frames`+1 frames at 64x64, extrapolated to 20 steps."""
+    from musev_b200.schema import preset_config
+    from musev_b200.synth import make_inputs, make_state_dict
+    from oracle.unet3d_oracle import UNet3DOracle
+    cores = threads or os.cpu_count() or 1
+    torch.set_num_threads(cores)
+    cfg = preset_config(preset)
+    o = UNet3DOracle(cfg, make_state_dict(cfg, seed=0))
+    inp = make_inputs(cfg, batch=2, frames=frames, h=LAT_H, w=LAT_W, n_vis_cond=1)
+    kw = dict(sample_index=inp["sample_index"], vision_conditon_frames_sample_index=inp["vision_conditon_frames_sample_index"],
+              sample_frame_rate=8)
+    t0 = time.perf_counter()
+    o(inp["sample"], 601, inp["encoder_hidden_states"], **kw)
+    dt = time.perf_counter() - t0
+    return {"value": frames / (dt * DDIM_STEPS), "unit": "frames/s", "cores": cores, "kind": "port",
+            "sample": f"1 oracle UNet3D forward (fp32, B=2 CFG, {frames}+1 frames, 64x64 latents, {preset}) = {dt:.1f} s; "
+                      f"x{DDIM_STEPS} DDIM steps extrapolated"}
+
+
+def run_reference(args):
+    """`--impl reference`: the reference's CPU path (the oracle port -- a Python reference cannot travel to the GPU box)."""
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    vals = []
+    cb = None
+    for i in range(args.warmup + args.steps):
+        cb = cpu_baseline(args.preset, frames=2)
+        if i >= args.warmup:
+            vals.append(cb["value"])
+    v = sum(vals) / len(vals)
+    cb["value"] = v
+    print(json.dumps({
+        "impl": "reference", "metric": METRIC, "value": v, "unit": "frames/s", "n_gpus": args.gpus, "steps": args.steps,
+        "warmup": args.warmup, "ms_per_step": 1000.0 * 2 / (v * 1.0) if v else None, "higher_is_better": True,
+        "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+        "config": {"workload": "config2 image2video 16-frame 512x512 20 DDIM steps (sampled: one 2+1-frame window-step per step)",
+                   "preset": args.preset},
+        "cpu_baseline": cb,
+        "e2e": {"value": v, "unit": "frames/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+    }), flush=True)
+
+
+def main():
+    args = parse()
+    if args.impl == "reference":
+        run_reference(args)
+        return
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if world != args.gpus:
+        if args.gpus != 1 or world != 1:
+            raise SystemExit(f"--gpus {args.gpus} but WORLD_SIZE={world}: launch with torch.distributed.run")
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    import torch.distributed as dist
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+
+    from musev_b200 import _capi
+    from musev_b200.flops import unet_forward_flops
+    from musev_b200.pipeline import ParallelDenoiser
+    from musev_b200.scheduler import SD15_DDIM_CONFIG, DDIMScheduler
+    from musev_b200.schema import preset_config
+    from musev_b200.synth import make_state_dict
+    from musev_b200.unet import UNet3DConditionModel
+
+    cfg = preset_config(args.preset)
+    unet = UNet3DConditionModel(cfg, device=dev, dtype=torch.float16)
+    sd = make_state_dict(cfg, seed=0, dtype=torch.float16)          # random-init weights of the named architecture
+    unet.load_state_dict(sd)
+    del sd
+    sched = DDIMScheduler(**SD15_DDIM_CONFIG)
+    den = ParallelDenoiser(unet, sched)
+    T = video_frames(world)
+    g = torch.Generator().manual_seed(1234)
+    lat_host = torch.randn(1, 4, T, LAT_H, LAT_W, generator=g).half().pin_memory()
+    cond_host = (torch.randn(1, 4, 1, LAT_H, LAT_W, generator=g) * 0.18215).half().pin_memory()
+    prompt_host = torch.randn(2, 77, cfg.cross_attention_dim, generator=g).half().pin_memory()
+    out_host = torch.empty(1, 4, T, LAT_H, LAT_W, dtype=torch.float16).pin_memory()
+    lat, cond, prompt = lat_host.to(dev), cond_host.to(dev), prompt_host.to(dev)
+
+    def one_step(latents, cond_l, prompt_e):
+        return den(latents, cond_l, prompt_e, num_inference_steps=DDIM_STEPS, guidance_scale=GUIDANCE,
+                   context_frames=WINDOW, context_overlap=OVERLAP, context_schedule="uniform_v2", motion_speed=8.0).latents
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    for _ in range(args.warmup):
+        one_step(lat, cond, prompt)
+    # ---- timed region 1: inputs resident in HBM
+    barrier()
+    sampler = ClockSampler(local)
+    if rank == 0:
+        sampler.start()
+    l0 = _capi.launch_count(-1)
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(args.steps):
+        res = one_step(lat, cond, prompt)
+    e1.record()
+    barrier()
+    launches = _capi.launch_count(-1) - l0
+    ms = torch.tensor([e0.elapsed_time(e1)], device=dev)
+    if world > 1:
+        dist.all_reduce(ms, op=dist.ReduceOp.MAX)
+    ms_total = float(ms.item())
+    # ---- timed region 2 (e2e): host buffers, H2D of the step's inputs and D2H of its result inside the region
+    barrier()
+    e2, e3 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e2.record()
+    for _ in range(args.steps):
+        l_d = lat_host.to(dev, non_blocking=True)
+        c_d = cond_host.to(dev, non_blocking=True)
+        p_d = prompt_host.to(dev, non_blocking=True)
+        r = one_step(l_d, c_d, p_d)
+        out_host.copy_(r, non_blocking=True)
+    e3.record()
+    barrier()
+    sampler.stop_flag = True
+    ms2 = torch.tensor([e2.elapsed_time(e3)], device=dev)
+    if world > 1:
+        dist.all_reduce(ms2, op=dist.ReduceOp.MAX)
+    ms2_total = float(ms2.item())
+    h2d = lat_host.numel() * 2 + cond_host.numel() * 2 + prompt_host.numel() * 2
+    d2h = out_host.numel() * 2
+
+    # ---- roofline of the dominant kernel (conv/linear tcgen05 GEMM): CUDA events around every launch of one more
+    # denoise step on the launching stream (separate pass so the event records do not perturb the timed regions)
+    roof = None
+    if rank == 0:
+        torch.cuda.synchronize()
+        _capi.profile_enable(True)
+        one_step(lat, cond, prompt)
+        prof = _capi.profile_collect()
+        _capi.profile_enable(False)
+        fl = unet_forward_flops(cfg, 2, WINDOW + 1, LAT_H, LAT_W)
+        n_fwd = DDIM_STEPS          # one window per rank -> one UNet forward per DDIM step
+        gemm_ms, gemm_n = prof["gemm"]["ms"], prof["gemm"]["launches"]
+        peaks = {}
+        try:
+            peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
+        except Exception:
+            pass
+        peak = peaks.get("bf16_tflops_sustained", 1400.0)
+        achieved = fl["gemm"] * n_fwd / (gemm_ms * 1e-3) / 1e12 if gemm_ms > 0 else None
+        roof = {"kernel": "conv_gemm_kernel (tcgen05 implicit-GEMM conv / linear)", "bound": "tensor",
+                "achieved": achieved, "peak": peak, "unit": "TFLOP/s", "frac": achieved / peak if achieved else None,
+                "peak_source": "MEASURED_PEAKS.json bf16_tflops_sustained" if peaks else "fallback 1.4 PFLOP/s sustained",
+                "traffic": None, "launches_per_step": gemm_n, "avg_launch_ms": gemm_ms / max(gemm_n, 1),
+                "algorithmic_tflop_per_forward": fl["gemm"] / 1e12,
+                "step_share": {k: round(v["ms"], 2) for k, v in prof.items()}}
+
+    if rank == 0:
+        frames = T * args.steps
+        value = frames / (ms_total * 1e-3)
+        e2e = frames / (ms2_total * 1e-3)
+        cb = None
+        if world == 1 and not args.skip_cpu_baseline:
+            try:
+                cb = cpu_baseline(args.preset)
+            except Exception as e:  # reported baseline only; never fail the GPU number on it
+                cb = {"error": str(e)}
+        fl_total = unet_forward_flops(cfg, 2, WINDOW + 1, LAT_H, LAT_W)["total"]
+        print(json.dumps({
+            "metric": METRIC, "value": value, "unit": "frames/s", "n_gpus": world, "steps": args.steps,
+            "warmup": args.warmup, "ms_per_step": ms_total / args.steps, "higher_is_better": True, "scaling": "weak",
+            "vs_baseline": None, "dtype": "f16 (fp32 accumulate)", "data": "synthetic",
+            "config": {"workload": f"config2 image2video 16-frame window 512x512, {DDIM_STEPS} DDIM steps, CFG, "
+                                   f"{args.preset} UNet3D" + ("" if world == 1 else f"; weak scaling: {T} frames = {world} windows (16, overlap 4), 1 per GPU"),
+                       "preset": args.preset, "frames": T, "latent_hw": [LAT_H, LAT_W], "ddim_steps": DDIM_STEPS,
+                       "windows": world, "parallelism": f"windows sharded over {world} GPU(s), 1 NCCL all-reduce/step",
+                       "l2_policy": "per-forward activation working set (~4 GB) >> 126 MB L2; no explicit flush",
+                       "achieved_tflops_whole_step": fl_total * DDIM_STEPS * args.steps * world / (ms_total * 1e-3) / 1e12},
+            "e2e": {"value": e2e, "unit": "frames/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h},
+            "gpu_launches": int(launches),
+            "clocks": sampler.summary(),
+            "roofline": roof,
+            "cpu_baseline": cb,
+        }), flush=True)
+    if world > 1:
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

@@ -82,6 +82,7 @@ typedef struct mvb_attention_desc {
   void* out; long long ldo;
   float out_scale;
   int accumulate;
+  int v_ones_col;  /* every V row holds 1.0 at column h*dp + d (dp > d): the P.V MMA also yields the softmax row sum */
 } mvb_attention_desc;
 
 int mvb_op_attention(const mvb_attention_desc* desc, void* stream);
@@ -186,6 +187,16 @@ const char* mvb_handle_error(mvb_handle* h);
 /* Debug aid for bisecting parity: layer outputs of the last forward, fp16 [rows, C] inside the caller's workspace. */
 int mvb_debug_num_taps(mvb_handle* h);
 int mvb_debug_tap(mvb_handle* h, int i, char* name, int name_cap, const void** ptr, long long* rows, int* C);
+
+
+/* ---------------------------------------------------------------------------------------------------------
+ * Accounting (used by bench.py). category: 0 conv/linear GEMM, 1 spatial attention, 2 temporal attention,
+ * 3 GroupNorm, 4 LayerNorm, 5 other; -1 = all. */
+long long mvb_launch_count(int category);
+/* When enabled every launcher brackets its kernel with two CUDA events on the launching stream. */
+void mvb_profile_enable(int on);
+/* Synchronises the device, sums the recorded event pairs per category (6 entries each) and clears them. */
+int mvb_profile_collect(double* ms_per_category, long long* scopes_per_category);
 
 #ifdef __cplusplus
 }

@@ -39,7 +39,7 @@ class AttentionDesc(C.Structure):
         ("k", C.c_void_p * 2), ("v", C.c_void_p * 2), ("ldkv", C.c_longlong * 2), ("kv_rows", C.c_longlong * 2),
         ("nk", C.c_int * 2), ("fdiv", C.c_int * 2), ("fmul", C.c_longlong * 2), ("fadd", C.c_longlong * 2),
         ("out", C.c_void_p), ("ldo", C.c_longlong),
-        ("out_scale", C.c_float), ("accumulate", C.c_int),
+        ("out_scale", C.c_float), ("accumulate", C.c_int), ("v_ones_col", C.c_int),
     ]
 
 
@@ -79,8 +79,32 @@ def _declare(l: C.CDLL) -> None:
     l.mvb_accumulate_window.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_void_p, C.c_int, C.c_int,
                                         C.c_int, C.c_void_p, C.c_int, C.c_void_p]
     l.mvb_accumulate_window.restype = C.c_int
+    l.mvb_launch_count.argtypes = [C.c_int]
+    l.mvb_launch_count.restype = C.c_longlong
+    l.mvb_profile_enable.argtypes = [C.c_int]
+    l.mvb_profile_enable.restype = None
+    l.mvb_profile_collect.argtypes = [C.POINTER(C.c_double), C.POINTER(C.c_longlong)]
+    l.mvb_profile_collect.restype = C.c_int
 
 
 def check(rc: int) -> None:
     if rc != 0:
         raise MvbError(f"musev_b200 error {rc}: {lib().mvb_last_error().decode()}")
+
+
+CATEGORIES = ("gemm", "attention", "temporal_attention", "groupnorm", "layernorm", "other")
+
+
+def launch_count(category: int = -1) -> int:
+    return int(lib().mvb_launch_count(category))
+
+
+def profile_enable(on: bool) -> None:
+    lib().mvb_profile_enable(int(on))
+
+
+def profile_collect():
+    ms = (C.c_double * 6)()
+    n = (C.c_longlong * 6)()
+    check(lib().mvb_profile_collect(ms, n))
+    return {c: dict(ms=ms[i], launches=int(n[i])) for i, c in enumerate(CATEGORIES)}

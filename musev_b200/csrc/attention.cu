@@ -12,8 +12,10 @@
 
 #include <cuda.h>
 #include <stdio.h>
+#include <stdlib.h>
 
 #include "ptx.cuh"
+#include "stats.cuh"
 
 namespace mvb {
 
@@ -31,9 +33,16 @@ struct AttnParams {
   __half* out;
   long long ldo;
   int accumulate;
+  int sum_in_v;   // V has a column of ones at index d (d % 8 == 0, d < dp): the PV MMA accumulates the softmax row sum
 };
 
 static constexpr int kAtomBytes = 128 * 128;  // 128 rows x 64 fp16
+
+__device__ __forceinline__ float fast_exp2(float x) {
+  float y;
+  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+  return y;
+}
 
 __device__ __forceinline__ void tile_info(const AttnParams& p, int j, int* seg, int* k0, int* valid) {
   const int t0 = (p.nk[0] + 127) / 128;
@@ -44,7 +53,7 @@ __device__ __forceinline__ void tile_info(const AttnParams& p, int j, int* seg, 
   }
 }
 
-__global__ void __launch_bounds__(192)
+__global__ void __launch_bounds__(192, 2)
 attention_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUtensorMap tmK0,
                  const __grid_constant__ CUtensorMap tmV0, const __grid_constant__ CUtensorMap tmK1,
                  const __grid_constant__ CUtensorMap tmV1, const __grid_constant__ AttnParams p) {
@@ -154,68 +163,65 @@ attention_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant_
     const int row = qd * 32 + lane;
     const uint32_t lane_off = (uint32_t)(qd * 32) << 16;
     float m = -INFINITY, l = 0.f;
+    const float sl2 = p.scale_log2;
     for (int j = 0; j < ntiles; ++j) {
       int seg, k0, valid;
       tile_info(p, j, &seg, &k0, &valid);
       mbar_wait(bar_s, j & 1);
       tc_fence_after();
-      float mx = -INFINITY;
-#pragma unroll 1
-      for (int c = 0; c < 4; ++c) {
-        uint32_t v[32];
-        tmem_ld32(tmem_S + lane_off + c * 32, v);
-        tmem_ld_wait();
+      // the whole S row (128 fp32) lives in registers: one TMEM pass per tile
+      uint32_t v[128];
+      tmem_ld32(tmem_S + lane_off + 0, *reinterpret_cast<uint32_t(*)[32]>(&v[0]));
+      tmem_ld32(tmem_S + lane_off + 32, *reinterpret_cast<uint32_t(*)[32]>(&v[32]));
+      tmem_ld32(tmem_S + lane_off + 64, *reinterpret_cast<uint32_t(*)[32]>(&v[64]));
+      tmem_ld32(tmem_S + lane_off + 96, *reinterpret_cast<uint32_t(*)[32]>(&v[96]));
+      tmem_ld_wait();
+      if (valid < 128) {
 #pragma unroll
-        for (int i = 0; i < 32; ++i)
-          if (c * 32 + i < valid) mx = fmaxf(mx, __uint_as_float(v[i]));
+        for (int i = 0; i < 128; ++i)
+          if (i >= valid) v[i] = 0xff800000u;   // -inf
       }
-      mx *= p.scale_log2;
+      float mx0 = __uint_as_float(v[0]), mx1 = __uint_as_float(v[1]);
+#pragma unroll
+      for (int i = 2; i < 128; i += 2) {
+        mx0 = fmaxf(mx0, __uint_as_float(v[i]));
+        mx1 = fmaxf(mx1, __uint_as_float(v[i + 1]));
+      }
+      const float mx = fmaxf(mx0, mx1) * sl2;
       const bool need = mx > m + 8.f;
       float alpha = 1.f;
-      if (need) { alpha = exp2f(m - mx); m = mx; }
+      if (need) { alpha = fast_exp2(m - mx); m = mx; }
       if (j > 0 && __any_sync(0xffffffffu, need)) {
-        for (int c0 = 0; c0 < p.dp; c0 += 32) {
-          if (c0 + 32 <= p.dp) {
-            uint32_t o[32];
-            tmem_ld32(tmem_O + lane_off + c0, o);
-            tmem_ld_wait();
+        for (int c0 = 0; c0 < p.dp; c0 += 16) {
+          uint32_t o[16];
+          tmem_ld16(tmem_O + lane_off + c0, o);
+          tmem_ld_wait();
 #pragma unroll
-            for (int i = 0; i < 32; ++i) o[i] = __float_as_uint(__uint_as_float(o[i]) * alpha);
-            tmem_st32(tmem_O + lane_off + c0, o);
-          } else {
-            uint32_t o[16];
-            tmem_ld16(tmem_O + lane_off + c0, o);
-            tmem_ld_wait();
-#pragma unroll
-            for (int i = 0; i < 16; ++i) o[i] = __float_as_uint(__uint_as_float(o[i]) * alpha);
-            tmem_st16(tmem_O + lane_off + c0, o);
-          }
+          for (int i = 0; i < 16; ++i) o[i] = __float_as_uint(__uint_as_float(o[i]) * alpha);
+          tmem_st16(tmem_O + lane_off + c0, o);
         }
         tmem_st_wait();
       }
       l *= alpha;
-#pragma unroll 1
-      for (int c = 0; c < 4; ++c) {
-        uint32_t v[32];
-        tmem_ld32(tmem_S + lane_off + c * 32, v);
-        tmem_ld_wait();
-        uint8_t* prow = sP + (c >> 1) * kAtomBytes + row * 128;
+      const float nm = -m;
+      float ls0 = 0.f, ls1 = 0.f;
 #pragma unroll
-        for (int g = 0; g < 4; ++g) {
-          __align__(16) __half2 ph[4];
+      for (int c = 0; c < 16; ++c) {   // 16 chunks of 8 keys = one 16-byte smem store each
+        __align__(16) __half2 ph[4];
 #pragma unroll
-          for (int e = 0; e < 4; ++e) {
-            const int col = c * 32 + g * 8 + 2 * e;
-            const float p0 = (col < valid) ? exp2f(__uint_as_float(v[g * 8 + 2 * e]) * p.scale_log2 - m) : 0.f;
-            const float p1 = (col + 1 < valid) ? exp2f(__uint_as_float(v[g * 8 + 2 * e + 1]) * p.scale_log2 - m) : 0.f;
-            ph[e] = __floats2half2_rn(p0, p1);
+        for (int e = 0; e < 4; ++e) {
+          const float p0 = fast_exp2(fmaf(__uint_as_float(v[c * 8 + 2 * e]), sl2, nm));
+          const float p1 = fast_exp2(fmaf(__uint_as_float(v[c * 8 + 2 * e + 1]), sl2, nm));
+          ph[e] = __floats2half2_rn(p0, p1);
+          if (!p.sum_in_v) {
             const float2 back = __half22float2(ph[e]);
-            l += back.x + back.y;
+            ls0 += back.x; ls1 += back.y;
           }
-          const int chunk = (c & 1) * 4 + g;
-          *reinterpret_cast<uint4*>(prow + ((chunk ^ (row & 7)) << 4)) = *reinterpret_cast<const uint4*>(ph);
         }
+        uint8_t* prow = sP + (c >> 3) * kAtomBytes + row * 128;
+        *reinterpret_cast<uint4*>(prow + (((c & 7) ^ (row & 7)) << 4)) = *reinterpret_cast<const uint4*>(ph);
       }
+      l += ls0 + ls1;
       fence_proxy_async();
       tc_fence_before();
       mbar_arrive(bar_p);
@@ -223,6 +229,13 @@ attention_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant_
     // epilogue
     mbar_wait(bar_o, 0);
     tc_fence_after();
+    if (p.sum_in_v) {
+      // the row sum was accumulated by the tensor core: V carries a column of ones at index d
+      uint32_t o[16];
+      tmem_ld16(tmem_O + lane_off + (p.d / 16) * 16, o);
+      tmem_ld_wait();
+      l = __uint_as_float(o[p.d % 16 == 8 ? 8 : 0]);
+    }
     const float inv = p.out_scale / l;
     const int qrow = q0 + row;
     const bool ok = qrow < p.Nq;
@@ -274,6 +287,7 @@ cudaError_t launch_attention(cudaStream_t stream, const AttnArgs& a, const char*
     if (s < a.nseg && g.nk < 1) { *err = "attention: empty KV segment"; return cudaErrorInvalidValue; }
   }
   p.out = a.out; p.ldo = a.ldo; p.accumulate = a.accumulate;
+  p.sum_in_v = (a.v_ones_col && a.dp > a.d) ? 1 : 0;
   if (p.natoms == 1) { p.sk = 2; p.sv = 1; }
   else if (p.natoms == 2) { p.sk = 2; p.sv = 1; }
   else { p.sk = 1; p.sv = 1; }
@@ -298,7 +312,12 @@ cudaError_t launch_attention(cudaStream_t stream, const AttnArgs& a, const char*
       !encode_map_2d(&tv1, s1.v, cols, (uint64_t)s1.rows, (uint64_t)s1.ld, 64, 128)) {
     *err = "cuTensorMapEncodeTiled(K/V) failed"; return cudaErrorInvalidValue;
   }
+  static const bool trace = getenv("MVB_TRACE") != nullptr;
+  if (trace)
+    fprintf(stderr, "MVB_TRACE attn NF=%d Nq=%d heads=%d d=%d nk0=%d nk1=%d acc=%d\n", a.NF, a.Nq, a.heads, a.d, p.nk[0],
+            p.nk[1], a.accumulate);
   dim3 grid((a.Nq + 127) / 128, a.heads, a.NF);
+  ProfScope prof(stream, KC_ATTENTION);
   attention_kernel<<<grid, 192, smem, stream>>>(tq, tk0, tv0, tk1, tv1, p);
   cudaError_t e = cudaGetLastError();
   if (e != cudaSuccess) *err = "attention_kernel launch";

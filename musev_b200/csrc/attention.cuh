@@ -32,6 +32,7 @@ struct AttnArgs {
   long long ldo;
   float out_scale;
   int accumulate;         // out += result
+  int v_ones_col;         // every V row holds 1.0 at column h*dp + d (needs dp > d): row sums come from the MMA
 };
 
 cudaError_t launch_attention(cudaStream_t stream, const AttnArgs& a, const char** err);

@@ -1,18 +1,21 @@
 // tcgen05 / TMA implicit-GEMM kernel. See conv_gemm.cuh for the math and the reference call sites.
 //
-// CTA = 256 threads, persistent over output tiles (128 rows x block_n columns):
+// CTA = 384 threads, persistent over output tiles (128 rows x block_n columns):
 //   warp 0   : TMA producer  -- per K block (64 channels of one tap) loads the A box {64, bw, bh, bn}
 //              (out-of-image taps are zero-filled by TMA = conv padding) and the weight tile {64, block_n}
 //   warp 1   : MMA issuer    -- one thread issues 4 x tcgen05.mma (K=16 each) per K block into TMEM
 //   warp 2   : TMEM allocator (512 columns = 2 accumulator stages x up to 256 fp32 columns)
-//   warps 4-7: epilogue      -- tcgen05.ld accumulator rows, bias / time-embedding / residual / GEGLU, fp16 store
+//   warps 4-11: epilogue     -- two warps per TMEM lane quarter, alternating 32-column chunks: tcgen05.ld accumulator
+//              rows, bias / time-embedding / residual (prefetched one chunk ahead) / GEGLU, fp16 store
 // Pipelines: smem ring (full/empty mbarriers, 4 stages) and TMEM double buffer (tmem_full/tmem_empty).
 #include "conv_gemm.cuh"
 
 #include <dlfcn.h>
 #include <stdio.h>
+#include <stdlib.h>
 
 #include "ptx.cuh"
+#include "stats.cuh"
 
 namespace mvb {
 
@@ -27,8 +30,24 @@ static constexpr int kSmemBytes = kStages * kStageBytes + 1024 /*align*/ + 256 /
 
 __device__ __forceinline__ float gelu_erf(float x) { return 0.5f * x * (1.f + erff(x * 0.70710678118654752440f)); }
 __device__ __forceinline__ float silu(float x) { return x / (1.f + __expf(-x)); }
+// exact-erf GELU (diffusers activations.py:89-102 uses F.gelu default) with erf from Abramowitz-Stegun 7.1.26
+// (|error| < 1.5e-7, far below the fp16 output rounding): one reciprocal, one exp2, a degree-5 polynomial.
+__device__ __forceinline__ float gelu_fast(float x) {
+  const float z = fabsf(x) * 0.70710678118654752440f;
+  const float t = __frcp_rn(fmaf(0.3275911f, z, 1.f));
+  float poly = fmaf(1.061405429f, t, -1.453152027f);
+  poly = fmaf(poly, t, 1.421413741f);
+  poly = fmaf(poly, t, -0.284496736f);
+  poly = fmaf(poly, t, 0.254829592f);
+  poly *= t;
+  float e;
+  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(e) : "f"(-z * z * 1.4426950408889634f));
+  const float erf_abs = fmaf(-poly, e, 1.f);
+  const float erf_v = copysignf(erf_abs, x);
+  return 0.5f * x * (1.f + erf_v);
+}
 
-__global__ void __launch_bounds__(256, 1)
+__global__ void __launch_bounds__(384, 1)
 conv_gemm_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__ CUtensorMap tmA1,
                  const __grid_constant__ CUtensorMap tmA2, const __grid_constant__ CUtensorMap tmA3,
                  const __grid_constant__ CUtensorMap tmB, const __grid_constant__ ConvGemmParams p) {
@@ -58,7 +77,7 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant
     }
     for (int s = 0; s < 2; ++s) {
       mbar_init(&tfull[s], 1);
-      mbar_init(&tempty[s], 4);
+      mbar_init(&tempty[s], 8);
     }
     fence_barrier_init();
   }
@@ -135,11 +154,14 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant
       }
     }
   } else if (warp >= 4) {
-    const int q = warp & 3;          // TMEM lane quarter this warp may read
+    // 8 epilogue warps: warp pair (q, half) owns TMEM lanes [32q, 32q+32) and every other 32-column chunk
+    const int q = warp & 3;
+    const int half = (warp - 4) >> 2;
     const int r = q * 32 + lane;     // accumulator row
     int as = 0;
     uint32_t aphase = 0;
     const int nout = p.geglu ? p.N / 2 : p.N;
+    const bool use_res = (p.res != nullptr) && !p.geglu && !p.out_f32;
     for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
       const int nt = tile % p.tiles_nn;
       const int mt = tile / p.tiles_nn;
@@ -153,12 +175,25 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant
       const bool row_ok = (w < p.W) && (h < p.H) && (n < p.NF);
       const long long m = ((long long)n * p.H + h) * p.W + w;
       const float* radd = p.rowadd ? p.rowadd + (long long)(m / p.rows_per_group) * p.ld_rowadd : nullptr;
+      const int ncol0 = nt * p.block_n;
+      const __half* res_row = use_res ? p.res + m * p.ld_res : nullptr;
+
+      // residual of the first chunk is requested before the accumulator is ready; later chunks one ahead
+      uint4 rcur[4] = {}, rnxt[4] = {};
+      auto load_res = [&](int c0, uint4 (&dst)[4]) {
+        if (!use_res || !row_ok) return;
+#pragma unroll
+        for (int g = 0; g < 4; ++g) {
+          const int nn = ncol0 + c0 + g * 8;
+          if (c0 + g * 8 < p.block_n && nn < p.N) dst[g] = __ldg(reinterpret_cast<const uint4*>(res_row + nn));
+        }
+      };
+      load_res(half * 32, rcur);
 
       mbar_wait(&tfull[as], aphase);
       tc_fence_after();
       const uint32_t t_row = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)as * kMaxBlockN;
-      const int ncol0 = nt * p.block_n;
-      for (int c0 = 0; c0 < p.block_n; c0 += 32) {
+      for (int c0 = half * 32; c0 < p.block_n; c0 += 64) {
         uint32_t v[32];
         const bool full32 = (c0 + 32 <= p.block_n);
         if (full32) {
@@ -169,68 +204,82 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant
 #pragma unroll
           for (int j = 0; j < 16; ++j) { v[j] = v16[j]; v[16 + j] = 0; }
         }
+        load_res(c0 + 64, rnxt);
         tmem_ld_wait();
-        if (!row_ok) continue;
-        const int ncols = full32 ? 32 : 16;
-        float f[32];
+        if (row_ok) {
+          const int ncols = full32 ? 32 : 16;
+          const int nbase = ncol0 + c0;
+          float f[32];
+          if (nbase + 32 <= p.N && ncols == 32) {
+            // vector path: bias / row-add as float4 (pointers are 16-byte aligned: nbase is a multiple of 16)
 #pragma unroll
-        for (int j = 0; j < 32; ++j) {
-          const int nn = ncol0 + c0 + j;
-          float x = __uint_as_float(v[j]);
-          if (j < ncols && nn < p.N) {
-            if (p.bias) x += __ldg(p.bias + nn);
-            if (radd) x += __ldg(radd + nn);
+            for (int g = 0; g < 8; ++g) {
+              float4 b = p.bias ? __ldg(reinterpret_cast<const float4*>(p.bias + nbase) + g) : make_float4(0, 0, 0, 0);
+              if (radd) {
+                const float4 a4 = __ldg(reinterpret_cast<const float4*>(radd + nbase) + g);
+                b.x += a4.x; b.y += a4.y; b.z += a4.z; b.w += a4.w;
+              }
+              f[g * 4 + 0] = __uint_as_float(v[g * 4 + 0]) + b.x;
+              f[g * 4 + 1] = __uint_as_float(v[g * 4 + 1]) + b.y;
+              f[g * 4 + 2] = __uint_as_float(v[g * 4 + 2]) + b.z;
+              f[g * 4 + 3] = __uint_as_float(v[g * 4 + 3]) + b.w;
+            }
+          } else {
+#pragma unroll
+            for (int j = 0; j < 32; ++j) {
+              const int nn = nbase + j;
+              float x = __uint_as_float(v[j]);
+              if (j < ncols && nn < p.N) {
+                if (p.bias) x += __ldg(p.bias + nn);
+                if (radd) x += __ldg(radd + nn);
+              }
+              f[j] = x;
+            }
           }
-          f[j] = x;
-        }
-        if (p.geglu) {
-          // packed chunk: columns [0,16) = value, [16,32) = gate of 16 consecutive output columns
-          const int oc = (ncol0 + c0) / 2;
-          if (oc < nout) {
-            __align__(16) __half o[16];
+          if (p.geglu) {
+            // packed chunk: columns [0,16) = value, [16,32) = gate of 16 consecutive output columns
+            const int oc = nbase / 2;
+            if (oc < nout) {
+              __align__(16) __half o[16];
 #pragma unroll
-            for (int j = 0; j < 16; ++j) o[j] = __float2half_rn(f[j] * gelu_erf(f[16 + j]));
-            uint4* dst = reinterpret_cast<uint4*>(p.out + m * p.ldc + oc);
-            dst[0] = reinterpret_cast<const uint4*>(o)[0];
-            dst[1] = reinterpret_cast<const uint4*>(o)[1];
-          }
-        } else {
+              for (int j = 0; j < 16; ++j) o[j] = __float2half_rn(f[j] * gelu_fast(f[16 + j]));
+              uint4* dst = reinterpret_cast<uint4*>(p.out + m * p.ldc + oc);
+              dst[0] = reinterpret_cast<const uint4*>(o)[0];
+              dst[1] = reinterpret_cast<const uint4*>(o)[1];
+            }
+          } else if (p.out_f32) {
 #pragma unroll
-          for (int g = 0; g < 4; ++g) {
-            const int nn = ncol0 + c0 + g * 8;
-            if (g * 8 < ncols && nn < p.N) {
-              __align__(16) __half o[8];
-              float rr[8];
-              if (p.out_f32) {
-                float* dstf = reinterpret_cast<float*>(p.out) + m * p.ldc + nn;
-                float of[8];
+            for (int g = 0; g < 8; ++g) {
+              const int nn = nbase + g * 4;
+              if (g * 4 < ncols && nn < p.N) {
+                float4 o4;
+                o4.x = f[g * 4 + 0] * p.alpha; o4.y = f[g * 4 + 1] * p.alpha;
+                o4.z = f[g * 4 + 2] * p.alpha; o4.w = f[g * 4 + 3] * p.alpha;
+                if (p.act == 1) { o4.x = silu(o4.x); o4.y = silu(o4.y); o4.z = silu(o4.z); o4.w = silu(o4.w); }
+                *reinterpret_cast<float4*>(reinterpret_cast<float*>(p.out) + m * p.ldc + nn) = o4;
+              }
+            }
+          } else {
+#pragma unroll
+            for (int g = 0; g < 4; ++g) {
+              const int nn = nbase + g * 8;
+              if (g * 8 < ncols && nn < p.N) {
+                __align__(16) __half o[8];
+                const __half* rh8 = reinterpret_cast<const __half*>(&rcur[g]);
 #pragma unroll
                 for (int j = 0; j < 8; ++j) {
                   float x = f[g * 8 + j] * p.alpha;
+                  if (use_res) x = fmaf(p.beta, __half2float(rh8[j]), x);
                   if (p.act == 1) x = silu(x);
-                  of[j] = x;
+                  o[j] = __float2half_rn(x);
                 }
-                reinterpret_cast<float4*>(dstf)[0] = make_float4(of[0], of[1], of[2], of[3]);
-                reinterpret_cast<float4*>(dstf)[1] = make_float4(of[4], of[5], of[6], of[7]);
-                continue;
+                *reinterpret_cast<uint4*>(p.out + m * p.ldc + nn) = *reinterpret_cast<const uint4*>(o);
               }
-              if (p.res) {
-                const uint4 rv = __ldg(reinterpret_cast<const uint4*>(p.res + m * p.ld_res + nn));
-                const __half* rh8 = reinterpret_cast<const __half*>(&rv);
-#pragma unroll
-                for (int j = 0; j < 8; ++j) rr[j] = __half2float(rh8[j]);
-              }
-#pragma unroll
-              for (int j = 0; j < 8; ++j) {
-                float x = f[g * 8 + j] * p.alpha;
-                if (p.res) x += p.beta * rr[j];
-                if (p.act == 1) x = silu(x);
-                o[j] = __float2half_rn(x);
-              }
-              *reinterpret_cast<uint4*>(p.out + m * p.ldc + nn) = *reinterpret_cast<const uint4*>(o);
             }
           }
         }
+#pragma unroll
+        for (int g = 0; g < 4; ++g) rcur[g] = rnxt[g];
       }
       tc_fence_before();
       __syncwarp();
@@ -346,11 +395,16 @@ static cudaError_t launch_common(cudaStream_t stream, const CUtensorMap* maps, i
   }
   const long long num_tiles = tiles_m * p.tiles_nn;
   const int grid = (int)(num_tiles < num_sms ? num_tiles : num_sms);
+  static const bool trace = getenv("MVB_TRACE") != nullptr;
+  if (trace)
+    fprintf(stderr, "MVB_TRACE gemm M=%lld N=%d K=%lld taps=%d block_n=%d tiles=%lld geglu=%d res=%d f32=%d\n",
+            (long long)p.W * p.H * p.NF, p.N, ktot, p.ntaps, p.block_n, num_tiles, p.geglu, p.res != nullptr, p.out_f32);
   const CUtensorMap& m0 = maps[0];
   const CUtensorMap& m1 = maps[nmaps > 1 ? 1 : 0];
   const CUtensorMap& m2 = maps[nmaps > 2 ? 2 : 0];
   const CUtensorMap& m3 = maps[nmaps > 3 ? 3 : 0];
-  conv_gemm_kernel<<<grid, 256, kSmemBytes, stream>>>(m0, m1, m2, m3, tmB, p);
+  ProfScope prof(stream, KC_GEMM);
+  conv_gemm_kernel<<<grid, 384, kSmemBytes, stream>>>(m0, m1, m2, m3, tmB, p);
   cudaError_t e = cudaGetLastError();
   if (e != cudaSuccess) *err = "conv_gemm_kernel launch";
   return e;

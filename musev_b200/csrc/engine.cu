@@ -47,6 +47,11 @@ __global__ void pack_vec_kernel(float* __restrict__ dst, int n, const TSrc* __re
   }
 }
 
+__global__ void set_ones_kernel(float* v_bias, int heads, int d, int dp) {
+  const int h = blockIdx.x * blockDim.x + threadIdx.x;
+  if (h < heads) v_bias[h * dp + d] = 1.f;
+}
+
 // ---------------------------------------------------------------------------------------------- construction
 Engine::Engine(const mvb_config& cfg, int device) : cfg_(cfg), device_(device) {
   heads_ = cfg.heads;
@@ -62,9 +67,11 @@ Engine::Engine(const mvb_config& cfg, int device) : cfg_(cfg), device_(device) {
   slab_counting_ = false;
   slab_off_ = 0;
   loaders_.clear();
+  ones_init_.clear();
   down_.clear(); up_.clear();
   temb_total_ = femb_total_ = 0;
   build();                                   // pass 2: assign pointers
+  for (const OnesInit& o : ones_init_) set_ones_kernel<<<1, 64>>>(o.v_bias, o.heads, o.d, o.dp);
   cudaMalloc(&zero_idx_dev_, 64 * sizeof(int));
   cudaMalloc(&fidx_dev_, 128 * sizeof(float));
 }
@@ -79,6 +86,15 @@ template <typename T> T* Engine::slab(size_t n) {
   const size_t a = (slab_off_ + 255) & ~size_t(255);
   slab_off_ = a + n * sizeof(T);
   return slab_counting_ ? nullptr : reinterpret_cast<T*>(slab_ + a);
+}
+
+// Bias for a fused projection whose last `heads*dp` rows are the (head-padded) V projection: zero except 1.0 at the
+// first padding column of every head, so that the P.V MMA also produces the softmax row sum. Null when dp == d.
+float* Engine::v_ones_bias(int rows_before_v, int total_rows, int d, int dp) {
+  if (dp <= d) return nullptr;
+  float* b = slab<float>(total_rows);
+  if (b) ones_init_.push_back({b + rows_before_v, heads_, d, dp});
+  return b;
 }
 
 Mat Engine::make_mat(int N, int K, bool bias) {
@@ -129,6 +145,7 @@ void Engine::build_tblock(const std::string& p, TBlock& b, int C, bool cross) {
   b.n2 = make_norm(p + ".norm2", C);
   b.n3 = make_norm(p + ".norm3", C);
   b.qkv1 = make_mat(3 * hd, C, false);
+  if (cross) b.qkv1.bias = v_ones_bias(2 * hd, 3 * hd, d, dp);
   reg_mat(p + ".attn1.to_q.weight", b.qkv1, 0, hd, 1, d, dp, C, C);
   reg_mat(p + ".attn1.to_k.weight", b.qkv1, hd, hd, 1, d, dp, C, C);
   reg_mat(p + ".attn1.to_v.weight", b.qkv1, 2 * hd, hd, 1, d, dp, C, C);
@@ -138,11 +155,13 @@ void Engine::build_tblock(const std::string& p, TBlock& b, int C, bool cross) {
     b.q2 = make_mat(hd, C, false);
     reg_mat(p + ".attn2.to_q.weight", b.q2, 0, hd, 1, d, dp, C, C);
     b.kv2 = make_mat(2 * hd, X, false);
+    b.kv2.bias = v_ones_bias(hd, 2 * hd, d, dp);
     reg_mat(p + ".attn2.to_k.weight", b.kv2, 0, hd, 1, d, dp, C, X);
     reg_mat(p + ".attn2.to_v.weight", b.kv2, hd, hd, 1, d, dp, C, X);
     b.has_ip = cfg_.ip_adapter_cross_attn != 0;
     if (b.has_ip) {
       b.kv2_ip = make_mat(2 * hd, X, false);
+      b.kv2_ip.bias = v_ones_bias(hd, 2 * hd, d, dp);
       reg_mat(p + ".attn2.to_k_ip.weight", b.kv2_ip, 0, hd, 1, d, dp, C, X);
       reg_mat(p + ".attn2.to_v_ip.weight", b.kv2_ip, hd, hd, 1, d, dp, C, X);
     }
@@ -209,6 +228,7 @@ void Engine::build_refer(const std::string& p, ReferAttn& r, int C) {
   const int H = heads_, d = C / H, dp = pad16(d), hd = H * dp;
   r.C = C; r.present = true;
   r.qkv = make_mat(3 * hd, C, false);
+  r.qkv.bias = v_ones_bias(2 * hd, 3 * hd, d, dp);
   reg_mat(p + ".to_q.weight", r.qkv, 0, hd, 1, d, dp, C, C);
   reg_mat(p + ".to_k.weight", r.qkv, hd, hd, 1, d, dp, C, C);
   reg_mat(p + ".to_v.weight", r.qkv, 2 * hd, hd, 1, d, dp, C, C);
@@ -542,9 +562,10 @@ struct Engine::Fwd {
       const size_t mk2 = mark();
       ln(h, M, C, 0.f, b.n1, nbuf);
       __half* qkv = alloc_h(M, 3 * hd);
-      { Epilogue ep; ep.out = qkv; ep.ldc = 3 * hd; gemm(nbuf, M, C, b.qkv1, ep, false); }
+      { Epilogue ep; ep.out = qkv; ep.ldc = 3 * hd; gemm(nbuf, M, C, b.qkv1, ep, b.qkv1.bias != nullptr); }
       __half* ao = alloc_h(M, C);
       AttnArgs aa{};
+      aa.v_ones_col = b.qkv1.bias != nullptr;
       aa.q = qkv; aa.ldq = 3 * hd; aa.NF = NF; aa.Nq = HW; aa.heads = Hh; aa.d = d; aa.dp = dp;
       aa.scale = 1.f / sqrtf((float)d);
       aa.nseg = 1;
@@ -569,9 +590,10 @@ struct Engine::Fwd {
       const int X = E->cfg_.cross_attention_dim;
       const long long Mt = (long long)B * a->n_text;
       __half* kv = alloc_h(Mt, 2 * hd);
-      { Epilogue ep; ep.out = kv; ep.ldc = 2 * hd; gemm(enc, Mt, X, b.kv2, ep, false); }
+      { Epilogue ep; ep.out = kv; ep.ldc = 2 * hd; gemm(enc, Mt, X, b.kv2, ep, b.kv2.bias != nullptr); }
       __half* ao = alloc_h(M, C);
       AttnArgs aa{};
+      aa.v_ones_col = b.kv2.bias != nullptr;
       aa.q = q; aa.ldq = hd; aa.NF = NF; aa.Nq = HW; aa.heads = Hh; aa.d = d; aa.dp = dp;
       aa.scale = 1.f / sqrtf((float)d);
       aa.nseg = 1;
@@ -581,7 +603,7 @@ struct Engine::Fwd {
       if (b.has_ip && clip && a->ip_adapter_scale > 0.f) {
         const long long Mc = (long long)B * a->n_clip;
         __half* kvi = alloc_h(Mc, 2 * hd);
-        { Epilogue ep; ep.out = kvi; ep.ldc = 2 * hd; gemm(clip, Mc, X, b.kv2_ip, ep, false); }
+        { Epilogue ep; ep.out = kvi; ep.ldc = 2 * hd; gemm(clip, Mc, X, b.kv2_ip, ep, b.kv2_ip.bias != nullptr); }
         aa.seg[0] = AttnSegment{kvi, kvi + hd, 2 * hd, Mc, a->n_clip, T, a->n_clip, 0};
         aa.out_scale = a->ip_adapter_scale; aa.accumulate = 1;
         attn(aa);
@@ -637,21 +659,23 @@ struct Engine::Fwd {
     __half* out = alloc_h(M, C);
     const size_t mk = mark();
     __half* qkv = alloc_h(M, 3 * hd);
-    { Epilogue ep; ep.out = qkv; ep.ldc = 3 * hd; gemm(x, M, C, r.qkv, ep, false); }
+    { Epilogue ep; ep.out = qkv; ep.ldc = 3 * hd; gemm(x, M, C, r.qkv, ep, r.qkv.bias != nullptr); }
     const long long Mr = (long long)B * nref;
     __half* kvr = alloc_h(Mr, 2 * hd);
     {
       Mat kvw = r.qkv;
       kvw.w = r.qkv.w ? r.qkv.w + (long long)hd * C : nullptr;
       kvw.N = 2 * hd;
+      kvw.bias = r.qkv.bias ? r.qkv.bias + hd : nullptr;
       Epilogue ep; ep.out = kvr; ep.ldc = 2 * hd;
-      gemm(ref, Mr, C, kvw, ep, false);
+      gemm(ref, Mr, C, kvw, ep, kvw.bias != nullptr);
     }
     __half* ao = alloc_h(M, C);
     AttnArgs aa{};
     aa.q = qkv; aa.ldq = 3 * hd; aa.NF = NF; aa.Nq = HW; aa.heads = Hh; aa.d = d; aa.dp = dp;
     aa.scale = 1.f / sqrtf((float)d);
     aa.nseg = 2;
+    aa.v_ones_col = r.qkv.bias != nullptr;
     aa.seg[0] = AttnSegment{kvr, kvr + hd, 2 * hd, Mr, nref, T, nref, 0};
     aa.seg[1] = AttnSegment{qkv + hd, qkv + 2 * hd, 3 * hd, M, HW, 1, HW, 0};
     aa.out = ao; aa.ldo = C; aa.out_scale = 1.f;

@@ -152,7 +152,9 @@ class Engine {
   std::string err_;
   std::vector<Tap> taps_;   // layer outputs of the last forward (pointers into the caller's workspace)
   std::unordered_map<std::string, Loader> loaders_;
-  std::vector<std::pair<size_t, void**>> slab_requests_;  // two-pass slab allocation
+  struct OnesInit { float* v_bias; int heads, d, dp; };
+  std::vector<OnesInit> ones_init_;   // V-part biases that carry the ones column used for MMA row sums
+  float* v_ones_bias(int rows_before_v, int total_rows, int d, int dp);
   char* slab_ = nullptr;
   size_t slab_bytes_ = 0, slab_off_ = 0;
   bool slab_counting_ = true;

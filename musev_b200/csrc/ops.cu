@@ -4,6 +4,8 @@
 
 #include <math.h>
 
+#include "stats.cuh"
+
 namespace mvb {
 
 __device__ __forceinline__ float silu_f(float x) { return x / (1.f + __expf(-x)); }
@@ -62,6 +64,7 @@ gn_stats_kernel(const __half* __restrict__ x0, int C0, const __half* __restrict_
 
 cudaError_t gn_stats(cudaStream_t s, const __half* x0, int C0, const __half* x1, int C1, int NF, int HW, int G,
                      float* part, int* chunks_out) {
+  ProfScope prof(s, KC_GROUPNORM);
   const int C = C0 + (x1 ? C1 : 0);
   if (!x1) C1 = 0;
   if ((C0 % 8) || (C1 % 8) || (C % G) || ((C / G) % 2)) return cudaErrorInvalidValue;
@@ -131,6 +134,7 @@ gn_apply_kernel(const __half* __restrict__ x0, int C0, const __half* __restrict_
 cudaError_t gn_apply(cudaStream_t s, const __half* x0, int C0, const __half* x1, int C1, int NF, int HW, int G,
                      const float* part, int chunks, int fps, float eps, const float* gamma, const float* beta, int silu,
                      __half* y) {
+  ProfScope prof(s, KC_GROUPNORM);
   if (!x1) C1 = 0;
   const int C = C0 + C1;
   if (fps < 1 || (NF % fps)) return cudaErrorInvalidValue;
@@ -202,6 +206,7 @@ layernorm_kernel(const __half* __restrict__ x, long long M, int C, float eps, co
 
 cudaError_t layernorm(cudaStream_t s, const __half* x, long long M, int C, float eps, const float* gamma,
                       const float* beta, __half* y) {
+  ProfScope prof(s, KC_LAYERNORM);
   if (C % 8) return cudaErrorInvalidValue;
   const int vecs = C / 8;
   const int rows_per_block = 8;
@@ -230,6 +235,7 @@ __global__ void upsample2x_kernel(const __half* __restrict__ x, int H, int W, in
   }
 }
 cudaError_t upsample2x(cudaStream_t s, const __half* x, int NF, int H, int W, int C, __half* y) {
+  ProfScope prof(s, KC_OTHER);
   if (C % 8) return cudaErrorInvalidValue;
   const long long total = (long long)NF * 4 * H * W * (C / 8);
   const int blocks = (int)((total + 255) / 256 < 148 * 16 ? (total + 255) / 256 : 148 * 16);
@@ -249,6 +255,7 @@ __global__ void add_kernel(const __half* __restrict__ a, const __half* __restric
   }
 }
 cudaError_t add_tensors(cudaStream_t s, const __half* a, const __half* b, long long n, __half* y) {
+  ProfScope prof(s, KC_OTHER);
   if (n % 8) return cudaErrorInvalidValue;
   const long long nv = n / 8;
   const int blocks = (int)((nv + 255) / 256 < 148 * 16 ? (nv + 255) / 256 : 148 * 16);
@@ -261,6 +268,7 @@ __global__ void silu_kernel(const __half* __restrict__ x, long long n, __half* _
     y[i] = __float2half_rn(silu_f(__half2float(x[i])));
 }
 cudaError_t silu_copy(cudaStream_t s, const __half* x, long long n, __half* y) {
+  ProfScope prof(s, KC_OTHER);
   const int blocks = (int)((n + 255) / 256 < 1024 ? (n + 255) / 256 : 1024);
   silu_kernel<<<blocks, 256, 0, s>>>(x, n, y);
   return cudaGetLastError();
@@ -286,6 +294,7 @@ __global__ void ncthw_to_tokens_kernel(const TIn* __restrict__ x, int B, int C, 
 }
 cudaError_t ncthw_to_tokens(cudaStream_t s, const void* x, int is_f32, int B, int C, int T, int HW, __half* y, int ldy,
                             float scale) {
+  ProfScope prof(s, KC_OTHER);
   dim3 grid((HW + 31) / 32, (C + 31) / 32, B * T), block(32, 8);
   if (is_f32) ncthw_to_tokens_kernel<float><<<grid, block, 0, s>>>((const float*)x, B, C, T, HW, y, ldy, scale);
   else ncthw_to_tokens_kernel<__half><<<grid, block, 0, s>>>((const __half*)x, B, C, T, HW, y, ldy, scale);
@@ -310,6 +319,7 @@ __global__ void tokens_to_ncthw_kernel(const __half* __restrict__ x, int ldx, in
   }
 }
 cudaError_t tokens_to_ncthw(cudaStream_t s, const __half* x, int ldx, int B, int C, int T, int HW, void* y, int is_f32) {
+  ProfScope prof(s, KC_OTHER);
   dim3 grid((HW + 31) / 32, (C + 31) / 32, B * T), block(32, 8);
   if (is_f32) tokens_to_ncthw_kernel<float><<<grid, block, 0, s>>>(x, ldx, B, C, T, HW, (float*)y);
   else tokens_to_ncthw_kernel<__half><<<grid, block, 0, s>>>(x, ldx, B, C, T, HW, (__half*)y);
@@ -335,6 +345,7 @@ __global__ void add_nchw_residual_kernel(__half* __restrict__ x, int C, int HW, 
   }
 }
 cudaError_t add_nchw_residual(cudaStream_t s, __half* x, int NF, int C, int HW, const void* r, int is_f32) {
+  ProfScope prof(s, KC_OTHER);
   dim3 grid((HW + 31) / 32, (C + 31) / 32, NF), block(32, 8);
   if (is_f32) add_nchw_residual_kernel<float><<<grid, block, 0, s>>>(x, C, HW, (const float*)r);
   else add_nchw_residual_kernel<__half><<<grid, block, 0, s>>>(x, C, HW, (const __half*)r);
@@ -367,6 +378,7 @@ __global__ void im2col_latent_kernel(const TIn* __restrict__ x, int B, int Cin, 
   }
 }
 cudaError_t im2col_latent(cudaStream_t s, const void* x, int is_f32, int B, int Cin, int T, int H, int W, __half* A) {
+  ProfScope prof(s, KC_OTHER);
   if (9 * Cin > 64) return cudaErrorInvalidValue;
   const long long total = (long long)B * T * H * W;
   const int blocks = (int)((total + 127) / 128);
@@ -386,6 +398,7 @@ __global__ void sinusoid_kernel(const float* __restrict__ values, int n, int dim
   }
 }
 cudaError_t sinusoid(cudaStream_t s, const float* values, int n, int dim, __half* out, int ld) {
+  ProfScope prof(s, KC_OTHER);
   sinusoid_kernel<<<(n * dim / 2 + 255) / 256, 256, 0, s>>>(values, n, dim, out, ld);
   return cudaGetLastError();
 }
@@ -406,6 +419,7 @@ __global__ void expand_rows_kernel(const __half* __restrict__ src, int B, int T,
 }
 cudaError_t expand_rows(cudaStream_t s, const __half* src, int B, int T, int D, const int* zero_t, int nzero, int act,
                         __half* out) {
+  ProfScope prof(s, KC_OTHER);
   expand_rows_kernel<<<(B * T * D + 255) / 256, 256, 0, s>>>(src, B, T, D, zero_t, nzero, act, out);
   return cudaGetLastError();
 }
@@ -500,6 +514,7 @@ temporal_attention_kernel(const __half* __restrict__ qkv, int ld, int B, int T, 
 
 cudaError_t temporal_attention(cudaStream_t s, const __half* qkv, int ld, int B, int T, int HW, int heads, int d, int dp,
                                float scale, __half* out, int ldo) {
+  ProfScope prof(s, KC_TEMPORAL_ATTN);
   if (T > 32 || (d % 8) || (dp % 8) || dp < d) return cudaErrorInvalidValue;
   const int D8 = dp / 8;
   const long long nprob = (long long)B * HW * heads;
@@ -560,6 +575,7 @@ cudaError_t fuse_cfg_ddim(cudaStream_t s, const float* eps_sum, const float* cou
                           void* latents_out, int is_f32, int B, int C, int T, int HW, int cfg, float guidance,
                           float alpha_t, float alpha_prev, int prediction_type, float clip_range, int use_clipped,
                           float std_dev, const float* noise, float* eps_out, float* x0_out) {
+  ProfScope prof(s, KC_OTHER);
   const long long n = (long long)B * C * T * HW;
   const int blocks = (int)((n + 255) / 256 < 148 * 8 ? (n + 255) / 256 : 148 * 8);
   if (is_f32)
@@ -591,6 +607,7 @@ __global__ void accumulate_window_kernel(float* __restrict__ eps_sum, int B2, in
 }
 cudaError_t accumulate_window(cudaStream_t s, float* eps_sum, int B2, int C, int T, int HW, const void* eps_win,
                               int is_f32, int Tw, int src_t0, const int* frames_dev, int nframes) {
+  ProfScope prof(s, KC_OTHER);
   const long long n = (long long)B2 * C * nframes * HW;
   const int blocks = (int)((n + 255) / 256 < 148 * 8 ? (n + 255) / 256 : 148 * 8);
   if (is_f32)

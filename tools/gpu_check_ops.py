@@ -31,20 +31,23 @@ def pad_heads(x, heads, d, dp):
     return o.view(M, heads * dp)
 
 
-def attn_case(NF, T, Nq, heads, d, nk1_mode, name):
+def attn_case(NF, T, Nq, heads, d, nk1_mode, name, ones=False):
     """self attention with K/V = own frame (+) vis-cond frame (frame 0 of each batch of T frames)."""
     dp = (d + 15) // 16 * 16
     M = NF * Nq
     q = torch.randn(M, heads * d, device=dev).half()
     k = torch.randn(M, heads * d, device=dev).half()
     v = torch.randn(M, heads * d, device=dev).half()
-    qkv = torch.cat([pad_heads(q, heads, d, dp), pad_heads(k, heads, d, dp), pad_heads(v, heads, d, dp)], dim=1).contiguous()
+    vp = pad_heads(v, heads, d, dp)
+    if ones:
+        vp.view(M, heads, dp)[:, :, d] = 1.0
+    qkv = torch.cat([pad_heads(q, heads, d, dp), pad_heads(k, heads, d, dp), vp], dim=1).contiguous()
     hd = heads * dp
     qv, kv, vv = qkv[:, :hd], qkv[:, hd:2 * hd], qkv[:, 2 * hd:]
     segs = [dict(k=kv, v=vv, nk=Nq, fdiv=1, fmul=Nq, fadd=0)]
     if nk1_mode == "viscond":
         segs.append(dict(k=kv, v=vv, nk=Nq, fdiv=T, fmul=T * Nq, fadd=0))
-    out = ops.attention(qv, segs, NF, Nq, heads, d, dp, d ** -0.5)
+    out = ops.attention(qv, segs, NF, Nq, heads, d, dp, d ** -0.5, v_ones_col=ones)
     torch.cuda.synchronize()
     qf = q.float().view(NF, Nq, heads, d).permute(0, 2, 1, 3)
     kf = k.float().view(NF, Nq, heads, d).permute(0, 2, 1, 3)
@@ -202,6 +205,8 @@ if __name__ == "__main__":
     guard(attn_case, 2, 1, 256, 2, 64, "none", "attn 2x2 tiles d=64")
     guard(attn_case, 2, 1, 128, 8, 40, "none", "attn d=40 (dp=48)")
     guard(attn_case, 4, 2, 256, 8, 40, "viscond", "attn d=40 viscond 2 segs")
+    guard(attn_case, 4, 2, 256, 8, 40, "viscond", "attn d=40 viscond 2 segs ONES", ones=True)
+    guard(attn_case, 2, 1, 200, 8, 40, "none", "attn d=40 Nq=200 (masked tail) ONES", ones=True)
     guard(attn_case, 4, 2, 256, 8, 80, "viscond", "attn d=80 viscond")
     guard(attn_case, 4, 2, 64, 8, 160, "viscond", "attn d=160 Nq=64 viscond")
     guard(attn_case, 6, 3, 1024, 8, 40, "viscond", "attn d=40 Nq=1024 viscond")
@@ -216,16 +221,17 @@ if __name__ == "__main__":
         M = NF * Nq
         qkv = torch.randn(M, 3 * heads * dp, device=dev).half()
         hd = heads * dp
+        qkv[:, 2 * hd:].view(M, heads, dp)[:, :, d] = 1.0
         segs = [dict(k=qkv[:, hd:2 * hd], v=qkv[:, 2 * hd:], nk=Nq, fdiv=1, fmul=Nq, fadd=0),
                 dict(k=qkv[:, hd:2 * hd], v=qkv[:, 2 * hd:], nk=Nq, fdiv=T, fmul=T * Nq, fadd=0)]
         out = torch.empty(M, heads * d, device=dev, dtype=torch.half)
         for _ in range(2):
-            ops.attention(qkv[:, :hd], segs, NF, Nq, heads, d, dp, d ** -0.5, out=out)
+            ops.attention(qkv[:, :hd], segs, NF, Nq, heads, d, dp, d ** -0.5, out=out, v_ones_col=True)
         torch.cuda.synchronize()
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         e0.record()
         for _ in range(5):
-            ops.attention(qkv[:, :hd], segs, NF, Nq, heads, d, dp, d ** -0.5, out=out)
+            ops.attention(qkv[:, :hd], segs, NF, Nq, heads, d, dp, d ** -0.5, out=out, v_ones_col=True)
         e1.record(); torch.cuda.synchronize()
         ms = e0.elapsed_time(e1) / 5
         fl = 4.0 * NF * heads * Nq * 2 * Nq * d

@@ -41,5 +41,5 @@ for _ in range(iters):
     out = model(x, torch.tensor(601), enc, **kw).sample
 e1.record()
 torch.cuda.synchronize()
-ms = e0.elapsed_time(e1) / iters
-print(f"[time] {preset} forward B=2 T={frames}+1 {hw}x{hw}: {ms:.2f} ms/forward (host {1000 * (time.time() - t0) / iters:.2f} ms)", flush=True)
+ms = e0.elapsed_time(e1) / max(iters, 1)
+print(f"[time] {preset} forward B=2 T={frames}+1 {hw}x{hw}: {ms:.2f} ms/forward (host {1000 * (time.time() - t0) / max(iters, 1):.2f} ms)", flush=True)
