@@ -73,7 +73,9 @@ attention_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant_
   uint64_t* bar_s = bars + 9;
   uint64_t* bar_p = bars + 10;
   uint64_t* bar_o = bars + 11;
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 12);
+  uint64_t* bar_sfree = bars + 12;  // softmax has pulled S_j into registers: S_{j+1} may overwrite the TMEM tile
+  uint64_t* bar_pv = bars + 13;     // P.V of tile j complete: P smem buffer reusable, O stable
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 14);
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int q0 = blockIdx.x * 128;
@@ -91,6 +93,8 @@ attention_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant_
     mbar_init(bar_s, 1);
     mbar_init(bar_p, 128);
     mbar_init(bar_o, 1);
+    mbar_init(bar_sfree, 128);
+    mbar_init(bar_pv, 1);
     fence_barrier_init();
   }
   if (warp == 1) {
@@ -109,17 +113,25 @@ attention_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant_
       mbar_expect_tx(bar_q, (uint32_t)tile_bytes);
       for (int a = 0; a < p.natoms; ++a)
         tma_load_2d(sQ + a * kAtomBytes, &tmQ, bar_q, h * p.dp + a * 64, f * p.Nq + q0);
-      for (int j = 0; j < ntiles; ++j) {
+      auto load_k = [&](int j) {
         int seg, k0, valid;
         tile_info(p, j, &seg, &k0, &valid);
         const long long row = (long long)(f / p.fdiv[seg]) * p.fmul[seg] + p.fadd[seg] + k0;
         const CUtensorMap* mk = seg ? &tmK1 : &tmK0;
-        const CUtensorMap* mv = seg ? &tmV1 : &tmV0;
-        const int ks = j % p.sk, vs = j % p.sv;
+        const int ks = j % p.sk;
         mbar_wait(&empty_k[ks], ((j / p.sk) & 1) ^ 1);
         mbar_expect_tx(&full_k[ks], (uint32_t)tile_bytes);
         for (int a = 0; a < p.natoms; ++a)
           tma_load_2d(sK + ks * tile_bytes + a * kAtomBytes, mk, &full_k[ks], h * p.dp + a * 64, (int)row);
+      };
+      load_k(0);
+      for (int j = 0; j < ntiles; ++j) {
+        if (j + 1 < ntiles) load_k(j + 1);     // K runs one tile ahead: S_{j+1} is computed under softmax j
+        int seg, k0, valid;
+        tile_info(p, j, &seg, &k0, &valid);
+        const long long row = (long long)(f / p.fdiv[seg]) * p.fmul[seg] + p.fadd[seg] + k0;
+        const CUtensorMap* mv = seg ? &tmV1 : &tmV0;
+        const int vs = j % p.sv;
         mbar_wait(&empty_v[vs], ((j / p.sv) & 1) ^ 1);
         mbar_expect_tx(&full_v[vs], (uint32_t)tile_bytes);
         for (int a = 0; a < p.natoms; ++a)
@@ -132,11 +144,11 @@ attention_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant_
       const uint32_t idesc_o = make_idesc_f16(128, p.dp, 0, 1);   // B (= V) is MN-major
       const int ksteps = p.dp / 16;
       mbar_wait(bar_q, 0);
-      for (int j = 0; j < ntiles; ++j) {
-        const int ks = j % p.sk, vs = j % p.sv;
+      const uint32_t aQ = smem_u32(sQ);
+      auto issue_s = [&](int j) {
+        const int ks = j % p.sk;
         mbar_wait(&full_k[ks], (j / p.sk) & 1);
         tc_fence_after();
-        const uint32_t aQ = smem_u32(sQ);
         const uint32_t aK = smem_u32(sK + ks * tile_bytes);
         for (int kk = 0; kk < ksteps; ++kk) {
           const uint32_t off = (uint32_t)(kk >> 2) * kAtomBytes + (uint32_t)(kk & 3) * 32;
@@ -144,6 +156,15 @@ attention_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant_
         }
         umma_commit(&empty_k[ks]);   // K stage free once S_j is done
         umma_commit(bar_s);
+      };
+      issue_s(0);
+      for (int j = 0; j < ntiles; ++j) {
+        // S_{j+1} is issued as soon as the softmax warps hold S_j in registers, i.e. it runs under softmax j
+        if (j + 1 < ntiles) {
+          mbar_wait(bar_sfree, j & 1);
+          issue_s(j + 1);
+        }
+        const int vs = j % p.sv;
         mbar_wait(&full_v[vs], (j / p.sv) & 1);
         mbar_wait(bar_p, j & 1);     // P_j in smem, O rescaled
         tc_fence_after();
@@ -155,6 +176,7 @@ attention_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant_
                       idesc_o, (j | k16) != 0);
         }
         umma_commit(&empty_v[vs]);
+        umma_commit(bar_pv);
         if (j == ntiles - 1) umma_commit(bar_o);
       }
     }
@@ -176,21 +198,30 @@ attention_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant_
       tmem_ld32(tmem_S + lane_off + 64, *reinterpret_cast<uint32_t(*)[32]>(&v[64]));
       tmem_ld32(tmem_S + lane_off + 96, *reinterpret_cast<uint32_t(*)[32]>(&v[96]));
       tmem_ld_wait();
+      tc_fence_before();
+      mbar_arrive(bar_sfree);            // the tensor core may start S_{j+1} now
       if (valid < 128) {
 #pragma unroll
         for (int i = 0; i < 128; ++i)
           if (i >= valid) v[i] = 0xff800000u;   // -inf
       }
-      float mx0 = __uint_as_float(v[0]), mx1 = __uint_as_float(v[1]);
+      float mxs[8];
 #pragma unroll
-      for (int i = 2; i < 128; i += 2) {
-        mx0 = fmaxf(mx0, __uint_as_float(v[i]));
-        mx1 = fmaxf(mx1, __uint_as_float(v[i + 1]));
+      for (int i = 0; i < 8; ++i) mxs[i] = __uint_as_float(v[i]);
+#pragma unroll
+      for (int i = 8; i < 128; i += 8) {
+#pragma unroll
+        for (int e = 0; e < 8; ++e) mxs[e] = fmaxf(mxs[e], __uint_as_float(v[i + e]));
       }
-      const float mx = fmaxf(mx0, mx1) * sl2;
+      const float mx = fmaxf(fmaxf(fmaxf(mxs[0], mxs[1]), fmaxf(mxs[2], mxs[3])),
+                             fmaxf(fmaxf(mxs[4], mxs[5]), fmaxf(mxs[6], mxs[7]))) * sl2;
       const bool need = mx > m + 8.f;
       float alpha = 1.f;
       if (need) { alpha = fast_exp2(m - mx); m = mx; }
+      if (j > 0) {
+        mbar_wait(bar_pv, (j - 1) & 1);  // P buffer free again and O_{j-1} final before it is rescaled
+        tc_fence_after();
+      }
       if (j > 0 && __any_sync(0xffffffffu, need)) {
         for (int c0 = 0; c0 < p.dp; c0 += 16) {
           uint32_t o[16];

@@ -714,7 +714,7 @@ bool Engine::run(const mvb_unet_args& a, Arena& ar, cudaStream_t s) {
     if (a.n_refer != expect) { err_ = "down_block_refer_embs: wrong number of maps"; return false; }
   }
   if (!ar.dry) taps_.clear();
-  f.gn_part = f.alloc_f((long long)NF * kGnMaxChunks * c.norm_num_groups * 2);
+  f.gn_part = f.alloc_f((long long)NF * (kGnMaxChunks + 1) * c.norm_num_groups * 2);
 
   // ---- embeddings (unet_3d_condition.py:887-937)
   __half* temb_rows = f.alloc_h(NF, temb);

@@ -16,18 +16,18 @@ struct alignas(16) Half8 {
 
 // ------------------------------------------------------------------------------------------------ GroupNorm
 // grid (chunks, NF); block 256. Thread owns a fixed 8-channel vector column and strides over pixels, so its
-// per-group accumulators stay in registers; groups are even-sized, so a half2 never straddles two groups.
+// accumulators stay in registers; groups are even-sized, so a half2 never straddles two groups. The block reduction is
+// deterministic (no atomics): per-(row slot, channel pair) partials go to smem and thread g sums group g in fixed order.
 __global__ void __launch_bounds__(256)
 gn_stats_kernel(const __half* __restrict__ x0, int C0, const __half* __restrict__ x1, int C1, int HW, int G,
                 float* __restrict__ part) {
-  extern __shared__ float sacc[];  // [G][2]
+  extern __shared__ float2 spair[];  // [rows_per_iter][C/2] (sum, sumsq) per channel pair
   const int C = C0 + C1;
   const int vecs = C / 8;
-  const int cpg = C / G;
+  const int pairs = C / 2;
+  const int cpg2 = (C / G) / 2;      // channel pairs per group
   const int f = blockIdx.y;
   const int chunks = gridDim.x;
-  for (int i = threadIdx.x; i < 2 * G; i += blockDim.x) sacc[i] = 0.f;
-  __syncthreads();
   const int cols_per_pass = vecs < (int)blockDim.x ? vecs : (int)blockDim.x;
   const int rows_per_iter = blockDim.x / cols_per_pass;
   const int r0 = threadIdx.x / cols_per_pass;
@@ -50,16 +50,22 @@ gn_stats_kernel(const __half* __restrict__ x0, int C0, const __half* __restrict_
         }
       }
 #pragma unroll
-      for (int j = 0; j < 4; ++j) {
-        const int g = (c + 2 * j) / cpg;
-        atomicAdd(&sacc[2 * g], s[j]);
-        atomicAdd(&sacc[2 * g + 1], q[j]);
-      }
+      for (int j = 0; j < 4; ++j) spair[(size_t)r0 * pairs + v * 4 + j] = make_float2(s[j], q[j]);
     }
   }
   __syncthreads();
-  for (int i = threadIdx.x; i < 2 * G; i += blockDim.x)
-    part[((size_t)f * chunks + blockIdx.x) * 2 * G + i] = sacc[i];
+  for (int g = threadIdx.x; g < G; g += blockDim.x) {
+    float s = 0.f, q = 0.f;
+    for (int r = 0; r < rows_per_iter; ++r)
+      for (int pc = g * cpg2; pc < (g + 1) * cpg2; ++pc) {
+        const float2 t = spair[(size_t)r * pairs + pc];
+        s += t.x;
+        q += t.y;
+      }
+    float* dst = part + ((size_t)f * chunks + blockIdx.x) * 2 * G + 2 * g;
+    dst[0] = s;
+    dst[1] = q;
+  }
 }
 
 cudaError_t gn_stats(cudaStream_t s, const __half* x0, int C0, const __half* x1, int C1, int NF, int HW, int G,
@@ -76,40 +82,63 @@ cudaError_t gn_stats(cudaStream_t s, const __half* x0, int C0, const __half* x1,
   if (chunks > kGnMaxChunks) chunks = kGnMaxChunks;
   if (chunks < 1) chunks = 1;
   *chunks_out = chunks;
-  gn_stats_kernel<<<dim3(chunks, NF), threads, 2 * G * sizeof(float), s>>>(x0, C0, x1, C1, HW, G, part);
+  const int cols = (C / 8) < threads ? (C / 8) : threads;
+  const size_t smem = (size_t)(threads / cols) * (C / 2) * sizeof(float2);
+  gn_stats_kernel<<<dim3(chunks, NF), threads, smem, s>>>(x0, C0, x1, C1, HW, G, part);
   return cudaGetLastError();
 }
 
-// grid (pixel blocks, NF); block 256. Block prologue reduces the partials of its stat group into smem mean/rstd.
+// Reduces the per-frame partials of one statistics group (fps consecutive frames) to mean / rstd per group:
+// stats[NF/fps][G][2]. grid NF/fps, block 32*? threads (one thread per group).
+__global__ void gn_finalize_kernel(const float* __restrict__ part, int chunks, int fps, int G, float count, float eps,
+                                   float* __restrict__ stats) {
+  const int sg = blockIdx.x;
+  for (int g = threadIdx.x; g < G; g += blockDim.x) {
+    float s = 0.f, q = 0.f;
+    for (int i = 0; i < fps * chunks; ++i) {
+      const float* pp = part + ((size_t)sg * fps * chunks + i) * 2 * G + 2 * g;
+      s += pp[0];
+      q += pp[1];
+    }
+    const float mean = s / count;
+    float var = q / count - mean * mean;
+    var = var < 0.f ? 0.f : var;
+    stats[((size_t)sg * G + g) * 2] = mean;
+    stats[((size_t)sg * G + g) * 2 + 1] = rsqrtf(var + eps);
+  }
+}
+
+// grid (pixel blocks, NF); block 256; each block streams ~64 KB.
 __global__ void __launch_bounds__(256)
 gn_apply_kernel(const __half* __restrict__ x0, int C0, const __half* __restrict__ x1, int C1, int HW, int G,
-                const float* __restrict__ part, int chunks, int fps, float eps, const float* __restrict__ gamma,
+                const float* __restrict__ stats, int fps, const float* __restrict__ gamma,
                 const float* __restrict__ beta, int silu, __half* __restrict__ y, int pix_per_block) {
   extern __shared__ float sm_gn[];  // mean[G], rstd[G]
   const int C = C0 + C1;
   const int cpg = C / G;
   const int f = blockIdx.y;
-  const int f0 = (f / fps) * fps;
   for (int g = threadIdx.x; g < G; g += blockDim.x) {
-    float s = 0.f, q = 0.f;
-    for (int ff = 0; ff < fps; ++ff)
-      for (int ch = 0; ch < chunks; ++ch) {
-        const float* pp = part + ((size_t)(f0 + ff) * chunks + ch) * 2 * G + 2 * g;
-        s += pp[0];
-        q += pp[1];
-      }
-    const float n = (float)fps * HW * cpg;
-    const float mean = s / n;
-    float var = q / n - mean * mean;
-    var = var < 0.f ? 0.f : var;
-    sm_gn[g] = mean;
-    sm_gn[G + g] = rsqrtf(var + eps);
+    sm_gn[g] = stats[((size_t)(f / fps) * G + g) * 2];
+    sm_gn[G + g] = stats[((size_t)(f / fps) * G + g) * 2 + 1];
   }
   __syncthreads();
   const int vecs = C / 8;
   const int p0 = blockIdx.x * pix_per_block;
   const int p1 = min(HW, p0 + pix_per_block);
   const int total = (p1 - p0) * vecs;
+  // a thread keeps the same channel vector when blockDim is a multiple of vecs; the affine terms are then loaded once
+  const bool fixed_col = (blockDim.x % vecs) == 0;
+  float ga[8], be[8];
+  if (fixed_col) {
+    const int c = (threadIdx.x % vecs) * 8;
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      const int g = (c + j) / cpg;
+      const float rstd = sm_gn[G + g];
+      ga[j] = rstd * __ldg(gamma + c + j);
+      be[j] = __ldg(beta + c + j) - sm_gn[g] * ga[j];
+    }
+  }
   for (int i = threadIdx.x; i < total; i += blockDim.x) {
     const int p = p0 + i / vecs;
     const int c = (i % vecs) * 8;
@@ -118,12 +147,17 @@ gn_apply_kernel(const __half* __restrict__ x0, int C0, const __half* __restrict_
     Half8 ov;
 #pragma unroll
     for (int j = 0; j < 4; ++j) {
-      const int cc = c + 2 * j;
-      const int g = cc / cpg;
-      const float mean = sm_gn[g], rstd = sm_gn[G + g];
       float2 t = __half22float2(hv.h[j]);
-      t.x = (t.x - mean) * rstd * __ldg(gamma + cc) + __ldg(beta + cc);
-      t.y = (t.y - mean) * rstd * __ldg(gamma + cc + 1) + __ldg(beta + cc + 1);
+      if (fixed_col) {
+        t.x = fmaf(t.x, ga[2 * j], be[2 * j]);
+        t.y = fmaf(t.y, ga[2 * j + 1], be[2 * j + 1]);
+      } else {
+        const int cc = c + 2 * j;
+        const int g = cc / cpg;
+        const float mean = sm_gn[g], rstd = sm_gn[G + g];
+        t.x = (t.x - mean) * rstd * __ldg(gamma + cc) + __ldg(beta + cc);
+        t.y = (t.y - mean) * rstd * __ldg(gamma + cc + 1) + __ldg(beta + cc + 1);
+      }
       if (silu) { t.x = silu_f(t.x); t.y = silu_f(t.y); }
       ov.h[j] = __floats2half2_rn(t.x, t.y);
     }
@@ -134,72 +168,94 @@ gn_apply_kernel(const __half* __restrict__ x0, int C0, const __half* __restrict_
 cudaError_t gn_apply(cudaStream_t s, const __half* x0, int C0, const __half* x1, int C1, int NF, int HW, int G,
                      const float* part, int chunks, int fps, float eps, const float* gamma, const float* beta, int silu,
                      __half* y) {
-  ProfScope prof(s, KC_GROUPNORM);
+  ProfScope prof(s, KC_GROUPNORM, 2);
   if (!x1) C1 = 0;
   const int C = C0 + C1;
-  if (fps < 1 || (NF % fps)) return cudaErrorInvalidValue;
-  // ~16 KB of fp16 per block
-  int ppb = (8192 + C - 1) / C;
+  if (fps < 1 || (NF % fps) || G > 64) return cudaErrorInvalidValue;
+  // mean / rstd live right behind the partial sums in the caller's scratch: NF*(kGnMaxChunks+1)*G*2 floats in total
+  float* stats = const_cast<float*>(part) + (size_t)NF * kGnMaxChunks * G * 2;
+  const float count = (float)fps * HW * (C / G);
+  gn_finalize_kernel<<<NF / fps, 32, 0, s>>>(part, chunks, fps, G, count, eps, stats);
+  // ~64 KB of fp16 per block, block size a multiple of the number of channel vectors when possible
+  const int vecs = C / 8;
+  int threads = 256;
+  if (vecs <= 256 && (256 % vecs) != 0) threads = (256 / vecs) * vecs;   // e.g. C=320: 240 threads, C=960: 240
+  if (threads < 64) threads = 256;
+  int ppb = (32768 + C - 1) / C;
   if (ppb < 1) ppb = 1;
-  const int blocks = (HW + ppb - 1) / ppb;
-  gn_apply_kernel<<<dim3(blocks, NF), 256, 2 * G * sizeof(float), s>>>(x0, C0, x1, C1, HW, G, part, chunks, fps, eps,
-                                                                       gamma, beta, silu, y, ppb);
+  int blocks = (HW + ppb - 1) / ppb;
+  while (blocks * NF < 2 * 148 && ppb > 1) { ppb = (ppb + 1) / 2; blocks = (HW + ppb - 1) / ppb; }
+  gn_apply_kernel<<<dim3(blocks, NF), threads, 2 * G * sizeof(float), s>>>(x0, C0, x1, C1, HW, G, stats, fps, gamma, beta,
+                                                                           silu, y, ppb);
   return cudaGetLastError();
 }
 
 // ------------------------------------------------------------------------------------------------ LayerNorm
-// one warp per row; C <= 2560 (10 Half8 per lane)
-template <int VPL>
+// one warp handles R rows at a time (R independent row streams in flight per lane); C <= 2560
+template <int VPL, int R>
 __global__ void __launch_bounds__(256)
 layernorm_kernel(const __half* __restrict__ x, long long M, int C, float eps, const float* __restrict__ gamma,
                  const float* __restrict__ beta, __half* __restrict__ y) {
-  const long long row = (long long)blockIdx.x * (blockDim.x / 32) + (threadIdx.x >> 5);
-  if (row >= M) return;
+  const long long row0 = ((long long)blockIdx.x * (blockDim.x / 32) + (threadIdx.x >> 5)) * R;
+  if (row0 >= M) return;
   const int lane = threadIdx.x & 31;
   const int vecs = C / 8;
-  float v[VPL][8];
-  float s = 0.f;
+  Half8 hv[R][VPL];
 #pragma unroll
-  for (int i = 0; i < VPL; ++i) {
-    const int vi = lane + i * 32;
-    if (vi < vecs) {
-      const Half8 hv = *reinterpret_cast<const Half8*>(x + row * C + vi * 8);
+  for (int r = 0; r < R; ++r) {
 #pragma unroll
-      for (int j = 0; j < 4; ++j) {
-        const float2 t = __half22float2(hv.h[j]);
-        v[i][2 * j] = t.x; v[i][2 * j + 1] = t.y;
-        s += t.x + t.y;
-      }
+    for (int i = 0; i < VPL; ++i) {
+      const int vi = lane + i * 32;
+      if (vi < vecs && row0 + r < M) hv[r][i] = *reinterpret_cast<const Half8*>(x + (row0 + r) * C + vi * 8);
     }
   }
 #pragma unroll
-  for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
-  const float mean = s / C;
-  float q = 0.f;
+  for (int r = 0; r < R; ++r) {
+    if (row0 + r >= M) break;
+    float v[VPL][8];
+    float s = 0.f;
 #pragma unroll
-  for (int i = 0; i < VPL; ++i) {
-    const int vi = lane + i * 32;
-    if (vi < vecs) {
+    for (int i = 0; i < VPL; ++i) {
+      const int vi = lane + i * 32;
+      if (vi < vecs) {
 #pragma unroll
-      for (int j = 0; j < 8; ++j) { const float d = v[i][j] - mean; q += d * d; }
-    }
-  }
-#pragma unroll
-  for (int o = 16; o > 0; o >>= 1) q += __shfl_xor_sync(0xffffffffu, q, o);
-  const float rstd = rsqrtf(q / C + eps);
-#pragma unroll
-  for (int i = 0; i < VPL; ++i) {
-    const int vi = lane + i * 32;
-    if (vi < vecs) {
-      Half8 ov;
-#pragma unroll
-      for (int j = 0; j < 4; ++j) {
-        const int c = vi * 8 + 2 * j;
-        const float a = (v[i][2 * j] - mean) * rstd * __ldg(gamma + c) + __ldg(beta + c);
-        const float b = (v[i][2 * j + 1] - mean) * rstd * __ldg(gamma + c + 1) + __ldg(beta + c + 1);
-        ov.h[j] = __floats2half2_rn(a, b);
+        for (int j = 0; j < 4; ++j) {
+          const float2 t = __half22float2(hv[r][i].h[j]);
+          v[i][2 * j] = t.x; v[i][2 * j + 1] = t.y;
+          s += t.x + t.y;
+        }
       }
-      *reinterpret_cast<Half8*>(y + row * C + vi * 8) = ov;
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
+    const float mean = s / C;
+    float q = 0.f;
+#pragma unroll
+    for (int i = 0; i < VPL; ++i) {
+      const int vi = lane + i * 32;
+      if (vi < vecs) {
+#pragma unroll
+        for (int j = 0; j < 8; ++j) { const float d = v[i][j] - mean; q += d * d; }
+      }
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) q += __shfl_xor_sync(0xffffffffu, q, o);
+    const float rstd = rsqrtf(q / C + eps);
+#pragma unroll
+    for (int i = 0; i < VPL; ++i) {
+      const int vi = lane + i * 32;
+      if (vi < vecs) {
+        Half8 ov;
+        const float4 g0 = __ldg(reinterpret_cast<const float4*>(gamma + vi * 8));
+        const float4 g1 = __ldg(reinterpret_cast<const float4*>(gamma + vi * 8) + 1);
+        const float4 b0 = __ldg(reinterpret_cast<const float4*>(beta + vi * 8));
+        const float4 b1 = __ldg(reinterpret_cast<const float4*>(beta + vi * 8) + 1);
+        ov.h[0] = __floats2half2_rn((v[i][0] - mean) * rstd * g0.x + b0.x, (v[i][1] - mean) * rstd * g0.y + b0.y);
+        ov.h[1] = __floats2half2_rn((v[i][2] - mean) * rstd * g0.z + b0.z, (v[i][3] - mean) * rstd * g0.w + b0.w);
+        ov.h[2] = __floats2half2_rn((v[i][4] - mean) * rstd * g1.x + b1.x, (v[i][5] - mean) * rstd * g1.y + b1.y);
+        ov.h[3] = __floats2half2_rn((v[i][6] - mean) * rstd * g1.z + b1.z, (v[i][7] - mean) * rstd * g1.w + b1.w);
+        *reinterpret_cast<Half8*>(y + (row0 + r) * C + vi * 8) = ov;
+      }
     }
   }
 }
@@ -209,12 +265,11 @@ cudaError_t layernorm(cudaStream_t s, const __half* x, long long M, int C, float
   ProfScope prof(s, KC_LAYERNORM);
   if (C % 8) return cudaErrorInvalidValue;
   const int vecs = C / 8;
-  const int rows_per_block = 8;
-  const unsigned blocks = (unsigned)((M + rows_per_block - 1) / rows_per_block);
-  if (vecs <= 32) layernorm_kernel<1><<<blocks, 256, 0, s>>>(x, M, C, eps, gamma, beta, y);
-  else if (vecs <= 64) layernorm_kernel<2><<<blocks, 256, 0, s>>>(x, M, C, eps, gamma, beta, y);
-  else if (vecs <= 160) layernorm_kernel<5><<<blocks, 256, 0, s>>>(x, M, C, eps, gamma, beta, y);
-  else if (vecs <= 320) layernorm_kernel<10><<<blocks, 256, 0, s>>>(x, M, C, eps, gamma, beta, y);
+  auto blocks_for = [&](int R) { return (unsigned)((M + 8LL * R - 1) / (8LL * R)); };
+  if (vecs <= 32) layernorm_kernel<1, 4><<<blocks_for(4), 256, 0, s>>>(x, M, C, eps, gamma, beta, y);
+  else if (vecs <= 64) layernorm_kernel<2, 4><<<blocks_for(4), 256, 0, s>>>(x, M, C, eps, gamma, beta, y);
+  else if (vecs <= 160) layernorm_kernel<5, 2><<<blocks_for(2), 256, 0, s>>>(x, M, C, eps, gamma, beta, y);
+  else if (vecs <= 320) layernorm_kernel<10, 1><<<blocks_for(1), 256, 0, s>>>(x, M, C, eps, gamma, beta, y);
   else return cudaErrorInvalidValue;
   return cudaGetLastError();
 }

@@ -11,6 +11,7 @@ static constexpr int kGnMaxChunks = 16;
 
 // GroupNorm statistics. x0 [NF, HW, C0] (+ optional x1 [NF, HW, C1] = channel concat). Writes per-frame partial
 // (sum, sumsq) per group: part[NF][chunks][G][2] fp32. Returns the number of chunks used through *chunks.
+// The scratch behind `part` must hold NF*(kGnMaxChunks+1)*G*2 floats (gn_apply keeps mean/rstd after the partials).
 cudaError_t gn_stats(cudaStream_t s, const __half* x0, int C0, const __half* x1, int C1, int NF, int HW, int G,
                      float* part, int* chunks);
 // y = [SiLU]((x - mean) * rstd * gamma + beta); statistics are reduced over `frames_per_stat` consecutive frames
