@@ -4,8 +4,9 @@
 //   warp 1      : TMEM allocator + single-thread MMA issuer
 //                   S = Q K^T   (M=128 queries, N=128 keys, K=dp)      -> TMEM columns [0,128)
 //                   O += P V    (M=128, N=dp, K=128 keys; V consumed MN-major straight from its row-major tile)
-//   warps 2..5  : softmax, one thread per query row: tcgen05.ld S, online max/sum with lazy rescaling of the TMEM
-//                 accumulator (only when the running max grows by > 2^8), P -> fp16 -> swizzled smem as MMA A operand
+//   warps 2..9  : softmax, two threads per query row (64 key columns each): tcgen05.ld S into registers, online max
+//                 (halves combined through smem) with lazy rescaling of the TMEM accumulator (only when the running
+//                 max grows by > 2^8), P -> fp16 -> swizzled smem as MMA A operand; row sums come from the MMA
 // Two CTAs are resident per SM when the head dimension allows (dp <= 64), so one CTA's softmax overlaps the other's
 // MMAs. With d = 40 the kernel is bound by the exp throughput of the SFUs, not by the tensor pipe.
 #include "attention.cuh"
@@ -53,7 +54,7 @@ __device__ __forceinline__ void tile_info(const AttnParams& p, int j, int* seg, 
   }
 }
 
-__global__ void __launch_bounds__(192, 2)
+__global__ void __launch_bounds__(320, 2)
 attention_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUtensorMap tmK0,
                  const __grid_constant__ CUtensorMap tmV0, const __grid_constant__ CUtensorMap tmK1,
                  const __grid_constant__ CUtensorMap tmV1, const __grid_constant__ AttnParams p) {
@@ -76,6 +77,7 @@ attention_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant_
   uint64_t* bar_sfree = bars + 12;  // softmax has pulled S_j into registers: S_{j+1} may overwrite the TMEM tile
   uint64_t* bar_pv = bars + 13;     // P.V of tile j complete: P smem buffer reusable, O stable
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 14);
+  float* smax = reinterpret_cast<float*>(bars + 16);   // [2 buffers][2 column halves][128 rows] row-max exchange
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int q0 = blockIdx.x * 128;
@@ -91,9 +93,9 @@ attention_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant_
       mbar_init(&full_v[s], 1); mbar_init(&empty_v[s], 1);
     }
     mbar_init(bar_s, 1);
-    mbar_init(bar_p, 128);
+    mbar_init(bar_p, 256);
     mbar_init(bar_o, 1);
-    mbar_init(bar_sfree, 128);
+    mbar_init(bar_sfree, 256);
     mbar_init(bar_pv, 1);
     fence_barrier_init();
   }
@@ -181,7 +183,9 @@ attention_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant_
       }
     }
   } else {
+    // 8 softmax warps: two threads per query row, each owning 64 of the 128 key columns of the tile
     const int qd = warp & 3;
+    const int ch = (warp - 2) >> 2;                 // column half: keys [64 ch, 64 ch + 64) = P atom `ch`
     const int row = qd * 32 + lane;
     const uint32_t lane_off = (uint32_t)(qd * 32) << 16;
     float m = -INFINITY, l = 0.f;
@@ -191,30 +195,32 @@ attention_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant_
       tile_info(p, j, &seg, &k0, &valid);
       mbar_wait(bar_s, j & 1);
       tc_fence_after();
-      // the whole S row (128 fp32) lives in registers: one TMEM pass per tile
-      uint32_t v[128];
-      tmem_ld32(tmem_S + lane_off + 0, *reinterpret_cast<uint32_t(*)[32]>(&v[0]));
-      tmem_ld32(tmem_S + lane_off + 32, *reinterpret_cast<uint32_t(*)[32]>(&v[32]));
-      tmem_ld32(tmem_S + lane_off + 64, *reinterpret_cast<uint32_t(*)[32]>(&v[64]));
-      tmem_ld32(tmem_S + lane_off + 96, *reinterpret_cast<uint32_t(*)[32]>(&v[96]));
+      uint32_t v[64];
+      tmem_ld32(tmem_S + lane_off + ch * 64, *reinterpret_cast<uint32_t(*)[32]>(&v[0]));
+      tmem_ld32(tmem_S + lane_off + ch * 64 + 32, *reinterpret_cast<uint32_t(*)[32]>(&v[32]));
       tmem_ld_wait();
       tc_fence_before();
       mbar_arrive(bar_sfree);            // the tensor core may start S_{j+1} now
       if (valid < 128) {
 #pragma unroll
-        for (int i = 0; i < 128; ++i)
-          if (i >= valid) v[i] = 0xff800000u;   // -inf
+        for (int i = 0; i < 64; ++i)
+          if (ch * 64 + i >= valid) v[i] = 0xff800000u;   // -inf
       }
       float mxs[8];
 #pragma unroll
       for (int i = 0; i < 8; ++i) mxs[i] = __uint_as_float(v[i]);
 #pragma unroll
-      for (int i = 8; i < 128; i += 8) {
+      for (int i = 8; i < 64; i += 8) {
 #pragma unroll
         for (int e = 0; e < 8; ++e) mxs[e] = fmaxf(mxs[e], __uint_as_float(v[i + e]));
       }
-      const float mx = fmaxf(fmaxf(fmaxf(mxs[0], mxs[1]), fmaxf(mxs[2], mxs[3])),
-                             fmaxf(fmaxf(mxs[4], mxs[5]), fmaxf(mxs[6], mxs[7]))) * sl2;
+      float mx = fmaxf(fmaxf(fmaxf(mxs[0], mxs[1]), fmaxf(mxs[2], mxs[3])),
+                       fmaxf(fmaxf(mxs[4], mxs[5]), fmaxf(mxs[6], mxs[7])));
+      // combine with the partner thread (other column half of the same row) through smem
+      float* xch = smax + (j & 1) * 256;
+      xch[ch * 128 + row] = mx;
+      named_bar_sync(1, 256);
+      mx = fmaxf(mx, xch[(ch ^ 1) * 128 + row]) * sl2;
       const bool need = mx > m + 8.f;
       float alpha = 1.f;
       if (need) { alpha = fast_exp2(m - mx); m = mx; }
@@ -223,7 +229,8 @@ attention_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant_
         tc_fence_after();
       }
       if (j > 0 && __any_sync(0xffffffffu, need)) {
-        for (int c0 = 0; c0 < p.dp; c0 += 16) {
+        // the two threads of a row split the O columns by 16-column chunk parity
+        for (int c0 = ch * 16; c0 < p.dp; c0 += 32) {
           uint32_t o[16];
           tmem_ld16(tmem_O + lane_off + c0, o);
           tmem_ld_wait();
@@ -236,8 +243,9 @@ attention_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant_
       l *= alpha;
       const float nm = -m;
       float ls0 = 0.f, ls1 = 0.f;
+      uint8_t* prow = sP + ch * kAtomBytes + row * 128;
 #pragma unroll
-      for (int c = 0; c < 16; ++c) {   // 16 chunks of 8 keys = one 16-byte smem store each
+      for (int c = 0; c < 8; ++c) {   // 8 chunks of 8 keys = one 16-byte smem store each
         __align__(16) __half2 ph[4];
 #pragma unroll
         for (int e = 0; e < 4; ++e) {
@@ -249,8 +257,7 @@ attention_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant_
             ls0 += back.x; ls1 += back.y;
           }
         }
-        uint8_t* prow = sP + (c >> 3) * kAtomBytes + row * 128;
-        *reinterpret_cast<uint4*>(prow + (((c & 7) ^ (row & 7)) << 4)) = *reinterpret_cast<const uint4*>(ph);
+        *reinterpret_cast<uint4*>(prow + ((c ^ (row & 7)) << 4)) = *reinterpret_cast<const uint4*>(ph);
       }
       l += ls0 + ls1;
       fence_proxy_async();
@@ -266,12 +273,17 @@ attention_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant_
       tmem_ld16(tmem_O + lane_off + (p.d / 16) * 16, o);
       tmem_ld_wait();
       l = __uint_as_float(o[p.d % 16 == 8 ? 8 : 0]);
+    } else {
+      float* xch = smax + (ntiles & 1) * 256;
+      xch[ch * 128 + row] = l;
+      named_bar_sync(1, 256);
+      l += xch[(ch ^ 1) * 128 + row];
     }
     const float inv = p.out_scale / l;
     const int qrow = q0 + row;
     const bool ok = qrow < p.Nq;
     __half* orow = p.out + ((long long)f * p.Nq + qrow) * p.ldo + h * p.d;
-    for (int c0 = 0; c0 < p.dp; c0 += 16) {
+    for (int c0 = ch * 16; c0 < p.dp; c0 += 32) {
       uint32_t o[16];
       tmem_ld16(tmem_O + lane_off + c0, o);
       tmem_ld_wait();
@@ -323,7 +335,7 @@ cudaError_t launch_attention(cudaStream_t stream, const AttnArgs& a, const char*
   else if (p.natoms == 2) { p.sk = 2; p.sv = 1; }
   else { p.sk = 1; p.sv = 1; }
   p.tmem_cols = (128 + a.dp <= 256) ? 256 : 512;
-  const int smem = (1 + p.sk + p.sv) * p.natoms * kAtomBytes + 2 * kAtomBytes + 1024 + 128;
+  const int smem = (1 + p.sk + p.sv) * p.natoms * kAtomBytes + 2 * kAtomBytes + 1024 + 128 + 2048;
   static int max_set = 0;
   if (smem > max_set) {
     cudaError_t e = cudaFuncSetAttribute(attention_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
@@ -349,7 +361,7 @@ cudaError_t launch_attention(cudaStream_t stream, const AttnArgs& a, const char*
             p.nk[1], a.accumulate);
   dim3 grid((a.Nq + 127) / 128, a.heads, a.NF);
   ProfScope prof(stream, KC_ATTENTION);
-  attention_kernel<<<grid, 192, smem, stream>>>(tq, tk0, tv0, tk1, tv1, p);
+  attention_kernel<<<grid, 320, smem, stream>>>(tq, tk0, tv0, tk1, tv1, p);
   cudaError_t e = cudaGetLastError();
   if (e != cudaSuccess) *err = "attention_kernel launch";
   return e;

@@ -26,7 +26,9 @@ static constexpr int kMaxBlockN = 256;
 static constexpr int kABytes = kBlockM * kBlockK * 2;        // 16 KB
 static constexpr int kBBytes = kMaxBlockN * kBlockK * 2;     // 32 KB
 static constexpr int kStageBytes = kABytes + kBBytes;
-static constexpr int kSmemBytes = kStages * kStageBytes + 1024 /*align*/ + 256 /*barriers*/;
+static constexpr int kStagingBufBytes = 128 * 64;               // 128 rows x 32 fp16 output columns
+static constexpr int kStagingBytes = 4 * kStagingBufBytes;       // 2 column-halves x double buffer
+static constexpr int kSmemBytes = kStages * kStageBytes + kStagingBytes + 1024 /*align*/ + 256 /*barriers*/;
 
 __device__ __forceinline__ float gelu_erf(float x) { return 0.5f * x * (1.f + erff(x * 0.70710678118654752440f)); }
 __device__ __forceinline__ float silu(float x) { return x / (1.f + __expf(-x)); }
@@ -50,10 +52,12 @@ __device__ __forceinline__ float gelu_fast(float x) {
 __global__ void __launch_bounds__(384, 1)
 conv_gemm_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__ CUtensorMap tmA1,
                  const __grid_constant__ CUtensorMap tmA2, const __grid_constant__ CUtensorMap tmA3,
-                 const __grid_constant__ CUtensorMap tmB, const __grid_constant__ ConvGemmParams p) {
+                 const __grid_constant__ CUtensorMap tmB, const __grid_constant__ CUtensorMap tmC,
+                 const __grid_constant__ ConvGemmParams p) {
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
-  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + kStages * kStageBytes);
+  uint8_t* staging = smem + kStages * kStageBytes;
+  uint64_t* bars = reinterpret_cast<uint64_t*>(staging + kStagingBytes);
   uint64_t* full = bars;                    // [kStages]
   uint64_t* empty = bars + kStages;         // [kStages]
   uint64_t* tfull = bars + 2 * kStages;     // [2]
@@ -69,6 +73,7 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant
     tma_prefetch_desc(&tmA2);
     tma_prefetch_desc(&tmA3);
     tma_prefetch_desc(&tmB);
+    tma_prefetch_desc(&tmC);
   }
   if (warp == 1 && lane == 0) {
     for (int s = 0; s < kStages; ++s) {
@@ -154,14 +159,18 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant
       }
     }
   } else if (warp >= 4) {
-    // 8 epilogue warps: warp pair (q, half) owns TMEM lanes [32q, 32q+32) and every other 32-column chunk
+    // 8 epilogue warps: warp (q, half) owns TMEM lanes [32q, 32q+32) and every other group of output columns.
+    // fp16 results leave through smem staging (64-byte swizzle) + TMA store: full-line coalesced writes, clipped by the
+    // tensor map at the image / matrix edges, so the store path needs no masks.
     const int q = warp & 3;
     const int half = (warp - 4) >> 2;
     const int r = q * 32 + lane;     // accumulator row
     int as = 0;
     uint32_t aphase = 0;
-    const int nout = p.geglu ? p.N / 2 : p.N;
     const bool use_res = (p.res != nullptr) && !p.geglu && !p.out_f32;
+    const bool issuer = (q == 0) && (lane == 0);
+    const int acc_step = p.geglu ? 64 : 32;             // accumulator columns consumed per 32 output columns
+    uint32_t chunk_iter = 0;
     for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
       const int nt = tile % p.tiles_nn;
       const int mt = tile / p.tiles_nn;
@@ -174,11 +183,10 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant
       const int w = tw * p.bw + rw, h = th * p.bh + rh, n = tn * p.bn + rn;
       const bool row_ok = (w < p.W) && (h < p.H) && (n < p.NF);
       const long long m = ((long long)n * p.H + h) * p.W + w;
-      const float* radd = p.rowadd ? p.rowadd + (long long)(m / p.rows_per_group) * p.ld_rowadd : nullptr;
+      const float* radd = (p.rowadd && row_ok) ? p.rowadd + (long long)(m / p.rows_per_group) * p.ld_rowadd : nullptr;
       const int ncol0 = nt * p.block_n;
       const __half* res_row = use_res ? p.res + m * p.ld_res : nullptr;
 
-      // residual of the first chunk is requested before the accumulator is ready; later chunks one ahead
       uint4 rcur[4] = {}, rnxt[4] = {};
       auto load_res = [&](int c0, uint4 (&dst)[4]) {
         if (!use_res || !row_ok) return;
@@ -188,30 +196,38 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant
           if (c0 + g * 8 < p.block_n && nn < p.N) dst[g] = __ldg(reinterpret_cast<const uint4*>(res_row + nn));
         }
       };
-      load_res(half * 32, rcur);
+      load_res(half * acc_step, rcur);
 
       mbar_wait(&tfull[as], aphase);
       tc_fence_after();
       const uint32_t t_row = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)as * kMaxBlockN;
-      for (int c0 = half * 32; c0 < p.block_n; c0 += 64) {
-        uint32_t v[32];
-        const bool full32 = (c0 + 32 <= p.block_n);
-        if (full32) {
-          tmem_ld32(t_row + c0, v);
-        } else {
-          uint32_t v16[16];
-          tmem_ld16(t_row + c0, v16);
+      for (int c0 = half * acc_step; c0 < p.block_n; c0 += 2 * acc_step) {
+        // accumulator -> f[32] = the 32 output columns of this chunk, bias / row-add applied
+        float f[32];
+        const int nbase = ncol0 + c0;
+        if (p.geglu) {
+          uint32_t va[32], vb[32];
+          tmem_ld32(t_row + c0, va);
+          tmem_ld32(t_row + c0 + 32, vb);
+          tmem_ld_wait();
+          // packed columns: [16 value | 16 gate] per 32 accumulator columns
 #pragma unroll
-          for (int j = 0; j < 16; ++j) { v[j] = v16[j]; v[16 + j] = 0; }
-        }
-        load_res(c0 + 64, rnxt);
-        tmem_ld_wait();
-        if (row_ok) {
-          const int ncols = full32 ? 32 : 16;
-          const int nbase = ncol0 + c0;
-          float f[32];
-          if (nbase + 32 <= p.N && ncols == 32) {
-            // vector path: bias / row-add as float4 (pointers are 16-byte aligned: nbase is a multiple of 16)
+          for (int hsel = 0; hsel < 2; ++hsel) {
+            const uint32_t* v = hsel ? vb : va;
+            const int nb = nbase + hsel * 32;
+#pragma unroll
+            for (int j = 0; j < 16; ++j) {
+              float val = __uint_as_float(v[j]), gate = __uint_as_float(v[16 + j]);
+              if (p.bias) { val += __ldg(p.bias + nb + j); gate += __ldg(p.bias + nb + 16 + j); }
+              f[hsel * 16 + j] = val * gelu_fast(gate);
+            }
+          }
+        } else {
+          uint32_t v[32];
+          tmem_ld32(t_row + c0, v);      // block_n is a multiple of 32
+          load_res(c0 + 2 * acc_step, rnxt);
+          tmem_ld_wait();
+          if (nbase + 32 <= p.N) {
 #pragma unroll
             for (int g = 0; g < 8; ++g) {
               float4 b = p.bias ? __ldg(reinterpret_cast<const float4*>(p.bias + nbase) + g) : make_float4(0, 0, 0, 0);
@@ -229,29 +245,20 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant
             for (int j = 0; j < 32; ++j) {
               const int nn = nbase + j;
               float x = __uint_as_float(v[j]);
-              if (j < ncols && nn < p.N) {
+              if (nn < p.N) {
                 if (p.bias) x += __ldg(p.bias + nn);
                 if (radd) x += __ldg(radd + nn);
               }
               f[j] = x;
             }
           }
-          if (p.geglu) {
-            // packed chunk: columns [0,16) = value, [16,32) = gate of 16 consecutive output columns
-            const int oc = nbase / 2;
-            if (oc < nout) {
-              __align__(16) __half o[16];
-#pragma unroll
-              for (int j = 0; j < 16; ++j) o[j] = __float2half_rn(f[j] * gelu_fast(f[16 + j]));
-              uint4* dst = reinterpret_cast<uint4*>(p.out + m * p.ldc + oc);
-              dst[0] = reinterpret_cast<const uint4*>(o)[0];
-              dst[1] = reinterpret_cast<const uint4*>(o)[1];
-            }
-          } else if (p.out_f32) {
+        }
+        if (p.out_f32) {
+          if (row_ok) {
 #pragma unroll
             for (int g = 0; g < 8; ++g) {
               const int nn = nbase + g * 4;
-              if (g * 4 < ncols && nn < p.N) {
+              if (nn < p.N) {
                 float4 o4;
                 o4.x = f[g * 4 + 0] * p.alpha; o4.y = f[g * 4 + 1] * p.alpha;
                 o4.z = f[g * 4 + 2] * p.alpha; o4.w = f[g * 4 + 3] * p.alpha;
@@ -259,24 +266,36 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant
                 *reinterpret_cast<float4*>(reinterpret_cast<float*>(p.out) + m * p.ldc + nn) = o4;
               }
             }
-          } else {
-#pragma unroll
-            for (int g = 0; g < 4; ++g) {
-              const int nn = nbase + g * 8;
-              if (g * 8 < ncols && nn < p.N) {
-                __align__(16) __half o[8];
-                const __half* rh8 = reinterpret_cast<const __half*>(&rcur[g]);
-#pragma unroll
-                for (int j = 0; j < 8; ++j) {
-                  float x = f[g * 8 + j] * p.alpha;
-                  if (use_res) x = fmaf(p.beta, __half2float(rh8[j]), x);
-                  if (p.act == 1) x = silu(x);
-                  o[j] = __float2half_rn(x);
-                }
-                *reinterpret_cast<uint4*>(p.out + m * p.ldc + nn) = *reinterpret_cast<const uint4*>(o);
-              }
-            }
           }
+        } else {
+          // finish in fp32, round to fp16, stage, store
+          uint8_t* buf = staging + (half * 2 + (chunk_iter & 1)) * kStagingBufBytes;
+          if (issuer) tma_store_wait_read<1>();            // the store that last read this buffer has drained
+          named_bar_sync(1 + half, 128);
+#pragma unroll
+          for (int g = 0; g < 4; ++g) {
+            __align__(16) __half o[8];
+            const __half* rh8 = reinterpret_cast<const __half*>(&rcur[g]);
+#pragma unroll
+            for (int j = 0; j < 8; ++j) {
+              float x = f[g * 8 + j];
+              if (!p.geglu) {
+                x *= p.alpha;
+                if (use_res) x = fmaf(p.beta, __half2float(rh8[j]), x);
+                if (p.act == 1) x = silu(x);
+              }
+              o[j] = __float2half_rn(x);
+            }
+            *reinterpret_cast<uint4*>(buf + r * 64 + ((g ^ ((r >> 1) & 3)) << 4)) = *reinterpret_cast<const uint4*>(o);
+          }
+          fence_proxy_async();
+          named_bar_sync(1 + half, 128);
+          if (issuer) {
+            const int oc = p.geglu ? nbase / 2 : nbase;
+            tma_store_4d(&tmC, buf, oc, tw * p.bw, th * p.bh, tn * p.bn);
+            tma_store_commit();
+          }
+          ++chunk_iter;
         }
 #pragma unroll
         for (int g = 0; g < 4; ++g) rcur[g] = rnxt[g];
@@ -286,6 +305,7 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant
       if (lane == 0) mbar_arrive(&tempty[as]);
       if (++as == 2) { as = 0; aphase ^= 1; }
     }
+    if (issuer) tma_store_wait_all();   // smem must stay valid until the last bulk store has read it
   }
 
   tc_fence_before();
@@ -311,8 +331,8 @@ EncodeTiledFn get_encode_fn() {
 }
 
 // rank-4 fp16 map, inner box 64 elements, 128-byte swizzle, zero fill out of bounds
-bool encode_map_4d(CUtensorMap* m, const void* ptr, const uint64_t dims[4], const uint64_t strides_elems[3],
-                   const uint32_t box[4]) {
+bool encode_map_4d_sw(CUtensorMap* m, const void* ptr, const uint64_t dims[4], const uint64_t strides_elems[3],
+                      const uint32_t box[4], CUtensorMapSwizzle swz) {
   EncodeTiledFn fn = get_encode_fn();
   if (!fn) return false;
   cuuint64_t gd[4] = {dims[0], dims[1], dims[2], dims[3]};
@@ -320,9 +340,13 @@ bool encode_map_4d(CUtensorMap* m, const void* ptr, const uint64_t dims[4], cons
   cuuint32_t bx[4] = {box[0], box[1], box[2], box[3]};
   cuuint32_t es[4] = {1, 1, 1, 1};
   CUresult r = fn(m, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 4, const_cast<void*>(ptr), gd, gs, bx, es,
-                  CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                  CU_TENSOR_MAP_INTERLEAVE_NONE, swz, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
                   CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
   return r == CUDA_SUCCESS;
+}
+bool encode_map_4d(CUtensorMap* m, const void* ptr, const uint64_t dims[4], const uint64_t strides_elems[3],
+                   const uint32_t box[4]) {
+  return encode_map_4d_sw(m, ptr, dims, strides_elems, box, CU_TENSOR_MAP_SWIZZLE_128B);
 }
 
 bool encode_map_2d(CUtensorMap* m, const void* ptr, uint64_t d0, uint64_t d1, uint64_t stride1_elems, uint32_t b0,
@@ -360,8 +384,8 @@ static int pick_block_n(int N, int geglu, long long tiles_m, int num_sms) {
   // candidates are multiples of 32 (GEGLU chunks) or 16; prefer few padded columns, then fewer waves
   int best = 0;
   double best_cost = 1e30;
-  for (int bn = 256; bn >= 16; bn -= 16) {
-    if (geglu && (bn % 32)) continue;
+  for (int bn = 256; bn >= 32; bn -= 32) {
+    if (geglu && (bn % 64)) continue;
     const int tn = ceil_div(N, bn);
     const long long tiles = tiles_m * tn;
     const long long waves = (tiles + num_sms - 1) / num_sms;
@@ -393,6 +417,19 @@ static cudaError_t launch_common(cudaStream_t stream, const CUtensorMap* maps, i
     *err = "cuTensorMapEncodeTiled(B) failed";
     return cudaErrorInvalidValue;
   }
+  // output tensor map {cols, W, H, NF}: mirrors the A box, 32 columns x 128 pixels, 64-byte swizzle
+  CUtensorMap tmC = tmB;
+  p.tma_store = ep.out_f32 ? 0 : 1;
+  if (p.tma_store) {
+    const int ncols = ep.geglu ? p.N / 2 : p.N;
+    const uint64_t dims[4] = {(uint64_t)ncols, (uint64_t)p.W, (uint64_t)p.H, (uint64_t)p.NF};
+    const uint64_t st[3] = {(uint64_t)ep.ldc, (uint64_t)ep.ldc * p.W, (uint64_t)ep.ldc * p.W * p.H};
+    const uint32_t box[4] = {32u, (uint32_t)p.bw, (uint32_t)p.bh, (uint32_t)p.bn};
+    if ((ep.ldc % 8) || !encode_map_4d_sw(&tmC, ep.out, dims, st, box, CU_TENSOR_MAP_SWIZZLE_64B)) {
+      *err = "cuTensorMapEncodeTiled(C) failed (output row stride must be a multiple of 8 elements)";
+      return cudaErrorInvalidValue;
+    }
+  }
   const long long num_tiles = tiles_m * p.tiles_nn;
   const int grid = (int)(num_tiles < num_sms ? num_tiles : num_sms);
   static const bool trace = getenv("MVB_TRACE") != nullptr;
@@ -404,7 +441,7 @@ static cudaError_t launch_common(cudaStream_t stream, const CUtensorMap* maps, i
   const CUtensorMap& m2 = maps[nmaps > 2 ? 2 : 0];
   const CUtensorMap& m3 = maps[nmaps > 3 ? 3 : 0];
   ProfScope prof(stream, KC_GEMM);
-  conv_gemm_kernel<<<grid, 384, kSmemBytes, stream>>>(m0, m1, m2, m3, tmB, p);
+  conv_gemm_kernel<<<grid, 384, kSmemBytes, stream>>>(m0, m1, m2, m3, tmB, tmC, p);
   cudaError_t e = cudaGetLastError();
   if (e != cudaSuccess) *err = "conv_gemm_kernel launch";
   return e;

@@ -40,6 +40,7 @@ struct ConvGemmParams {
   int geglu;  // packed columns are [16 value | 16 gate] chunks: out = value * gelu_erf(gate)
   int act;    // 0 none, 1 SiLU
   int out_f32;  // store fp32 instead of fp16 (embedding tables)
+  int tma_store;  // fp16 output leaves through smem staging + TMA store (coalesced), else direct 16-byte stores
 };
 
 struct ASource {

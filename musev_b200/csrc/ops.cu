@@ -92,14 +92,23 @@ cudaError_t gn_stats(cudaStream_t s, const __half* x0, int C0, const __half* x1,
 // stats[NF/fps][G][2]. grid NF/fps, block 32*? threads (one thread per group).
 __global__ void gn_finalize_kernel(const float* __restrict__ part, int chunks, int fps, int G, float count, float eps,
                                    float* __restrict__ stats) {
+  // 8 lanes per group walk the partials in a fixed interleaved order, then a fixed shuffle tree: deterministic
   const int sg = blockIdx.x;
-  for (int g = threadIdx.x; g < G; g += blockDim.x) {
-    float s = 0.f, q = 0.f;
-    for (int i = 0; i < fps * chunks; ++i) {
+  const int g = threadIdx.x >> 3, sub = threadIdx.x & 7;
+  float s = 0.f, q = 0.f;
+  if (g < G) {
+    for (int i = sub; i < fps * chunks; i += 8) {
       const float* pp = part + ((size_t)sg * fps * chunks + i) * 2 * G + 2 * g;
       s += pp[0];
       q += pp[1];
     }
+  }
+#pragma unroll
+  for (int o = 4; o > 0; o >>= 1) {
+    s += __shfl_xor_sync(0xffffffffu, s, o);
+    q += __shfl_xor_sync(0xffffffffu, q, o);
+  }
+  if (g < G && sub == 0) {
     const float mean = s / count;
     float var = q / count - mean * mean;
     var = var < 0.f ? 0.f : var;
@@ -175,7 +184,7 @@ cudaError_t gn_apply(cudaStream_t s, const __half* x0, int C0, const __half* x1,
   // mean / rstd live right behind the partial sums in the caller's scratch: NF*(kGnMaxChunks+1)*G*2 floats in total
   float* stats = const_cast<float*>(part) + (size_t)NF * kGnMaxChunks * G * 2;
   const float count = (float)fps * HW * (C / G);
-  gn_finalize_kernel<<<NF / fps, 32, 0, s>>>(part, chunks, fps, G, count, eps, stats);
+  gn_finalize_kernel<<<NF / fps, ((G * 8 + 31) / 32) * 32, 0, s>>>(part, chunks, fps, G, count, eps, stats);
   // ~64 KB of fp16 per block, block size a multiple of the number of channel vectors when possible
   const int vecs = C / 8;
   int threads = 256;
@@ -480,117 +489,187 @@ cudaError_t expand_rows(cudaStream_t s, const __half* src, int B, int T, int D, 
 }
 
 // ------------------------------------------------------------------------------------------------ temporal attention
-// One warp per (batch, pixel, head): T <= 32 query frames, lane i owns query i. K/V rows staged in smem as fp16.
-template <int D8>  // ceil(d / 8)
+// ---- tensor-core version: one warp per (batch, pixel, head); T <= 32 frames padded to a 32x32 score tile.
+// S = Q K^T and O = P V run on mma.sync m16n8k16 (the problem is 32 x 32 x dp per warp: far too small for tcgen05's
+// 128-row tiles), so the kernel is left with its HBM traffic: q,k,v read once, o written once.
+__device__ __forceinline__ void ldsm_x4(uint32_t (&r)[4], const void* p) {
+  const uint32_t a = static_cast<uint32_t>(__cvta_generic_to_shared(p));
+  asm volatile("ldmatrix.sync.aligned.m8n8.x4.shared.b16 {%0,%1,%2,%3}, [%4];" : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]) : "r"(a));
+}
+__device__ __forceinline__ void ldsm_x4_trans(uint32_t (&r)[4], const void* p) {
+  const uint32_t a = static_cast<uint32_t>(__cvta_generic_to_shared(p));
+  asm volatile("ldmatrix.sync.aligned.m8n8.x4.trans.shared.b16 {%0,%1,%2,%3}, [%4];" : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]) : "r"(a));
+}
+__device__ __forceinline__ void mma16816(float (&c)[4], const uint32_t (&a)[4], uint32_t b0, uint32_t b1) {
+  asm volatile("mma.sync.aligned.m16n8k16.row.col.f32.f16.f16.f32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, {%0,%1,%2,%3};"
+               : "+f"(c[0]), "+f"(c[1]), "+f"(c[2]), "+f"(c[3])
+               : "r"(a[0]), "r"(a[1]), "r"(a[2]), "r"(a[3]), "r"(b0), "r"(b1));
+}
+__device__ __forceinline__ uint32_t pack_h2(float a, float b) {
+  const __half2 h = __floats2half2_rn(a, b);
+  return *reinterpret_cast<const uint32_t*>(&h);
+}
+
+template <int DP>
 __global__ void __launch_bounds__(128)
-temporal_attention_kernel(const __half* __restrict__ qkv, int ld, int B, int T, int HW, int heads, int d, int dp,
-                          float scale, __half* __restrict__ out, int ldo) {
-  extern __shared__ __align__(16) __half sm_ta[];
+temporal_attention_mma_kernel(const __half* __restrict__ qkv, int ld, int B, int T, int HW, int heads, int d,
+                              float scale_log2, __half* __restrict__ out, int ldo) {
+  constexpr int DS = DP + 8;            // padded smem row (keeps ldmatrix rows on distinct banks, 16-byte aligned)
+  constexpr int D8 = DP / 8;
+  extern __shared__ __align__(16) __half sm_tm[];
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const int wpb = blockDim.x >> 5;
-  const long long prob = (long long)blockIdx.x * wpb + warp;
+  const long long prob = (long long)blockIdx.x * (blockDim.x >> 5) + warp;
   const long long nprob = (long long)B * HW * heads;
   if (prob >= nprob) return;
   const int h = (int)(prob % heads);
   const long long bp = prob / heads;
   const int pix = (int)(bp % HW);
   const int b = (int)(bp / HW);
-  constexpr int DS = D8 * 8;                       // padded row length in smem
-  __half* sq = sm_ta + (size_t)warp * 3 * T * DS;     // q rows [T][DS]
-  __half* sk = sq + T * DS;
-  __half* sv = sk + T * DS;
-  const int hd = heads * dp;
-  // cooperative load: T rows x D8 vectors for q, k, v
-  for (int i = lane; i < T * D8; i += 32) {
+  __half* sq = sm_tm + (size_t)warp * 3 * 32 * DS;
+  __half* sk = sq + 32 * DS;
+  __half* sv = sk + 32 * DS;
+  const int hd = heads * DP;
+  for (int i = lane; i < 32 * D8; i += 32) {
     const int t = i / D8, v8 = i % D8;
-    const __half* row = qkv + (((size_t)b * T + t) * HW + pix) * ld + h * dp + v8 * 8;
-    *reinterpret_cast<uint4*>(sq + t * DS + v8 * 8) = *reinterpret_cast<const uint4*>(row);
-    *reinterpret_cast<uint4*>(sk + t * DS + v8 * 8) = *reinterpret_cast<const uint4*>(row + hd);
-    *reinterpret_cast<uint4*>(sv + t * DS + v8 * 8) = *reinterpret_cast<const uint4*>(row + 2 * hd);
+    uint4 q4 = make_uint4(0, 0, 0, 0), k4 = q4, v4 = q4;
+    if (t < T) {
+      const __half* row = qkv + (((size_t)b * T + t) * HW + pix) * ld + h * DP + v8 * 8;
+      q4 = *reinterpret_cast<const uint4*>(row);
+      k4 = *reinterpret_cast<const uint4*>(row + hd);
+      v4 = *reinterpret_cast<const uint4*>(row + 2 * hd);
+    }
+    *reinterpret_cast<uint4*>(sq + t * DS + v8 * 8) = q4;
+    *reinterpret_cast<uint4*>(sk + t * DS + v8 * 8) = k4;
+    *reinterpret_cast<uint4*>(sv + t * DS + v8 * 8) = v4;
   }
   __syncwarp();
-  const int qi = lane < T ? lane : T - 1;
-  float sc[32];
+  // ---- S = Q K^T (32 x 32)
+  float sacc[2][4][4];
 #pragma unroll
-  for (int j = 0; j < 32; ++j) sc[j] = 0.f;
-  for (int v8 = 0; v8 < D8; ++v8) {
-    const uint4 qv = *reinterpret_cast<const uint4*>(sq + qi * DS + v8 * 8);
-    const __half2* q2 = reinterpret_cast<const __half2*>(&qv);
-    float qf[8];
+  for (int mt = 0; mt < 2; ++mt)
 #pragma unroll
-    for (int e = 0; e < 4; ++e) { const float2 t2 = __half22float2(q2[e]); qf[2 * e] = t2.x; qf[2 * e + 1] = t2.y; }
+    for (int nt = 0; nt < 4; ++nt)
 #pragma unroll
-    for (int j = 0; j < 32; ++j) {
-      if (j < T) {
-        const uint4 kv = *reinterpret_cast<const uint4*>(sk + j * DS + v8 * 8);
-        const __half2* k2 = reinterpret_cast<const __half2*>(&kv);
+      for (int e = 0; e < 4; ++e) sacc[mt][nt][e] = 0.f;
 #pragma unroll
-        for (int e = 0; e < 4; ++e) {
-          const float2 t2 = __half22float2(k2[e]);
-          sc[j] = fmaf(qf[2 * e], t2.x, sc[j]);
-          sc[j] = fmaf(qf[2 * e + 1], t2.y, sc[j]);
-        }
+  for (int ks = 0; ks < DP / 16; ++ks) {
+    uint32_t a[2][4], bk[2][4];
+#pragma unroll
+    for (int mt = 0; mt < 2; ++mt) ldsm_x4(a[mt], sq + (mt * 16 + (lane & 15)) * DS + ks * 16 + (lane >> 4) * 8);
+#pragma unroll
+    for (int np = 0; np < 2; ++np)   // two key tiles (16 keys) per ldmatrix.x4
+      ldsm_x4(bk[np], sk + (np * 16 + (lane & 7) + ((lane >> 4) << 3)) * DS + ks * 16 + ((lane >> 3) & 1) * 8);
+#pragma unroll
+    for (int mt = 0; mt < 2; ++mt)
+#pragma unroll
+      for (int nt = 0; nt < 4; ++nt) mma16816(sacc[mt][nt], a[mt], bk[nt >> 1][(nt & 1) * 2], bk[nt >> 1][(nt & 1) * 2 + 1]);
+  }
+  // ---- softmax over the key axis (rows: mt*16 + lane/4 and +8; columns nt*8 + 2*(lane%4) + {0,1})
+  float inv[2][2];
+  uint32_t pa[2][2][4];   // P as A fragments: [m tile][key step of 16]
+#pragma unroll
+  for (int mt = 0; mt < 2; ++mt) {
+    float mx[2] = {-INFINITY, -INFINITY};
+#pragma unroll
+    for (int nt = 0; nt < 4; ++nt)
+#pragma unroll
+      for (int e = 0; e < 4; ++e) {
+        const int col = nt * 8 + 2 * (lane & 3) + (e & 1);
+        if (col >= T) sacc[mt][nt][e] = -INFINITY;
+        mx[e >> 1] = fmaxf(mx[e >> 1], sacc[mt][nt][e]);
       }
+#pragma unroll
+    for (int r = 0; r < 2; ++r) {
+      mx[r] = fmaxf(mx[r], __shfl_xor_sync(0xffffffffu, mx[r], 1));
+      mx[r] = fmaxf(mx[r], __shfl_xor_sync(0xffffffffu, mx[r], 2));
+    }
+    float sum[2] = {0.f, 0.f};
+#pragma unroll
+    for (int nt = 0; nt < 4; ++nt)
+#pragma unroll
+      for (int e = 0; e < 4; ++e) {
+        const float pv = exp2f((sacc[mt][nt][e] - mx[e >> 1]) * scale_log2);
+        sacc[mt][nt][e] = pv;
+        sum[e >> 1] += pv;
+      }
+#pragma unroll
+    for (int r = 0; r < 2; ++r) {
+      sum[r] += __shfl_xor_sync(0xffffffffu, sum[r], 1);
+      sum[r] += __shfl_xor_sync(0xffffffffu, sum[r], 2);
+      inv[mt][r] = 1.f / sum[r];
+    }
+#pragma unroll
+    for (int k2 = 0; k2 < 2; ++k2) {
+      pa[mt][k2][0] = pack_h2(sacc[mt][2 * k2][0], sacc[mt][2 * k2][1]);
+      pa[mt][k2][1] = pack_h2(sacc[mt][2 * k2][2], sacc[mt][2 * k2][3]);
+      pa[mt][k2][2] = pack_h2(sacc[mt][2 * k2 + 1][0], sacc[mt][2 * k2 + 1][1]);
+      pa[mt][k2][3] = pack_h2(sacc[mt][2 * k2 + 1][2], sacc[mt][2 * k2 + 1][3]);
     }
   }
-  float mx = -INFINITY;
+  __syncwarp();   // all lanes are done reading Q: its buffer becomes the output staging area
+  // ---- O = P V, 16 output columns per step
 #pragma unroll
-  for (int j = 0; j < 32; ++j) if (j < T) mx = fmaxf(mx, sc[j] * scale);
-  float sum = 0.f;
+  for (int n0 = 0; n0 < DP; n0 += 16) {
+    float oacc[2][2][4];
 #pragma unroll
-  for (int j = 0; j < 32; ++j) {
-    if (j < T) { sc[j] = __expf(sc[j] * scale - mx); sum += sc[j]; }
-  }
-  const float inv = 1.f / sum;
-  for (int v8 = 0; v8 < D8; ++v8) {
-    float o[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+    for (int mt = 0; mt < 2; ++mt)
 #pragma unroll
-    for (int j = 0; j < 32; ++j) {
-      if (j < T) {
-        const uint4 vv = *reinterpret_cast<const uint4*>(sv + j * DS + v8 * 8);
-        const __half2* v2 = reinterpret_cast<const __half2*>(&vv);
+      for (int nt = 0; nt < 2; ++nt)
 #pragma unroll
-        for (int e = 0; e < 4; ++e) {
-          const float2 t2 = __half22float2(v2[e]);
-          o[2 * e] = fmaf(sc[j], t2.x, o[2 * e]);
-          o[2 * e + 1] = fmaf(sc[j], t2.y, o[2 * e + 1]);
-        }
+        for (int e = 0; e < 4; ++e) oacc[mt][nt][e] = 0.f;
+#pragma unroll
+    for (int k2 = 0; k2 < 2; ++k2) {
+      uint32_t bv[4];
+      ldsm_x4_trans(bv, sv + (k2 * 16 + (lane & 7) + ((lane >> 3) & 1) * 8) * DS + n0 + (lane >> 4) * 8);
+#pragma unroll
+      for (int mt = 0; mt < 2; ++mt) {
+        mma16816(oacc[mt][0], pa[mt][k2], bv[0], bv[1]);
+        mma16816(oacc[mt][1], pa[mt][k2], bv[2], bv[3]);
       }
     }
-    if (lane < T && v8 * 8 < d) {
-      __align__(16) __half oh[8];
 #pragma unroll
-      for (int e = 0; e < 8; ++e) oh[e] = __float2half_rn(o[e] * inv);
-      *reinterpret_cast<uint4*>(out + (((size_t)b * T + lane) * HW + pix) * ldo + h * d + v8 * 8) =
-          *reinterpret_cast<const uint4*>(oh);
-    }
+    for (int mt = 0; mt < 2; ++mt)
+#pragma unroll
+      for (int nt = 0; nt < 2; ++nt) {
+        const int col = n0 + nt * 8 + 2 * (lane & 3);
+        const int r_lo = mt * 16 + (lane >> 2);
+        *reinterpret_cast<uint32_t*>(sq + r_lo * DS + col) = pack_h2(oacc[mt][nt][0] * inv[mt][0], oacc[mt][nt][1] * inv[mt][0]);
+        *reinterpret_cast<uint32_t*>(sq + (r_lo + 8) * DS + col) = pack_h2(oacc[mt][nt][2] * inv[mt][1], oacc[mt][nt][3] * inv[mt][1]);
+      }
+  }
+  __syncwarp();
+  const int dv = d / 8;
+  for (int i = lane; i < T * dv; i += 32) {
+    const int t = i / dv, v8 = i % dv;
+    *reinterpret_cast<uint4*>(out + (((size_t)b * T + t) * HW + pix) * ldo + h * d + v8 * 8) =
+        *reinterpret_cast<const uint4*>(sq + t * DS + v8 * 8);
   }
 }
 
 cudaError_t temporal_attention(cudaStream_t s, const __half* qkv, int ld, int B, int T, int HW, int heads, int d, int dp,
                                float scale, __half* out, int ldo) {
   ProfScope prof(s, KC_TEMPORAL_ATTN);
-  if (T > 32 || (d % 8) || (dp % 8) || dp < d) return cudaErrorInvalidValue;
-  const int D8 = dp / 8;
+  if (T > 32 || T < 1 || (d % 8) || (dp % 16) || dp < d) return cudaErrorInvalidValue;
   const long long nprob = (long long)B * HW * heads;
   const int wpb = 4;
   const unsigned blocks = (unsigned)((nprob + wpb - 1) / wpb);
-  const size_t smem = (size_t)wpb * 3 * T * dp * sizeof(__half);
-#define MVB_TA(N)                                                                                              \
-  case N: {                                                                                                     \
-    static bool set##N = false;                                                                                 \
-    if (!set##N) {                                                                                              \
-      cudaFuncSetAttribute(temporal_attention_kernel<N>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024); \
-      set##N = true;                                                                                            \
-    }                                                                                                           \
-    temporal_attention_kernel<N><<<blocks, wpb * 32, smem, s>>>(qkv, ld, B, T, HW, heads, d, dp, scale, out, ldo); \
-    break;                                                                                                      \
+  const float sl2 = scale * 1.4426950408889634f;
+#define MVB_TAM(N)                                                                                                  \
+  case N: {                                                                                                          \
+    const size_t smem = (size_t)wpb * 3 * 32 * (N + 8) * sizeof(__half);                                             \
+    static bool set##N = false;                                                                                      \
+    if (!set##N) {                                                                                                   \
+      cudaFuncSetAttribute(temporal_attention_mma_kernel<N>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem); \
+      set##N = true;                                                                                                 \
+    }                                                                                                                \
+    temporal_attention_mma_kernel<N><<<blocks, wpb * 32, smem, s>>>(qkv, ld, B, T, HW, heads, d, sl2, out, ldo);    \
+    break;                                                                                                           \
   }
-  switch (D8) {
-    MVB_TA(1) MVB_TA(2) MVB_TA(4) MVB_TA(6) MVB_TA(10) MVB_TA(20)
+  switch (dp) {
+    MVB_TAM(16) MVB_TAM(32) MVB_TAM(48) MVB_TAM(64) MVB_TAM(80) MVB_TAM(96) MVB_TAM(160)
     default: return cudaErrorInvalidValue;
   }
-#undef MVB_TA
+#undef MVB_TAM
   return cudaGetLastError();
 }
 
