@@ -38,6 +38,28 @@ struct AttnParams {
 };
 
 static constexpr int kAtomBytes = 128 * 128;  // 128 rows x 64 fp16
+static constexpr int kPolyOf8 = 3;             // of every 8 column pairs, this many take the FMA-pipe exp2
+
+// 2^x for a pair of arguments on the FMA / ALU pipes (no SFU): round-to-nearest split x = n + f, |f| <= 0.5, degree-4
+// polynomial for 2^f (relative error < 5e-5, an order of magnitude below the fp16 rounding of P), exponent patched in
+// with integer arithmetic. Used for a fixed share of the softmax columns so that the SFU (16 ex2/clk/SM), which bounds
+// this kernel at head dim 40, and the FMA pipe work in parallel.
+__device__ __forceinline__ void poly_exp2_pair(float a0, float a1, float& p0, float& p1) {
+  const F2 a = f2_make(fmaxf(a0, -125.f), fmaxf(a1, -125.f));
+  const F2 magic = f2_make(12582912.f, 12582912.f);
+  const F2 t = f2_add(a, magic);
+  const F2 nf = f2_add(t, f2_make(-12582912.f, -12582912.f));
+  const F2 f = f2_fma(nf, f2_make(-1.f, -1.f), a);
+  F2 q = f2_fma(f, f2_make(0.00961812911f, 0.00961812911f), f2_make(0.0555041087f, 0.0555041087f));
+  q = f2_fma(q, f, f2_make(0.240226507f, 0.240226507f));
+  q = f2_fma(q, f, f2_make(0.693147181f, 0.693147181f));
+  q = f2_fma(q, f, f2_make(1.f, 1.f));
+  float q0, q1, t0, t1;
+  f2_get(q, q0, q1);
+  f2_get(t, t0, t1);
+  p0 = __int_as_float(__float_as_int(q0) + (__float_as_int(t0) << 23));
+  p1 = __int_as_float(__float_as_int(q1) + (__float_as_int(t1) << 23));
+}
 
 __device__ __forceinline__ float fast_exp2(float x) {
   float y;
@@ -241,7 +263,7 @@ attention_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant_
         tmem_st_wait();
       }
       l *= alpha;
-      const float nm = -m;
+      const F2 sl2x2 = f2_make(sl2, sl2), nmx2 = f2_make(-m, -m);
       float ls0 = 0.f, ls1 = 0.f;
       uint8_t* prow = sP + ch * kAtomBytes + row * 128;
 #pragma unroll
@@ -249,8 +271,15 @@ attention_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant_
         __align__(16) __half2 ph[4];
 #pragma unroll
         for (int e = 0; e < 4; ++e) {
-          const float p0 = fast_exp2(fmaf(__uint_as_float(v[c * 8 + 2 * e]), sl2, nm));
-          const float p1 = fast_exp2(fmaf(__uint_as_float(v[c * 8 + 2 * e + 1]), sl2, nm));
+          float a0, a1;
+          f2_get(f2_fma(f2_make(__uint_as_float(v[c * 8 + 2 * e]), __uint_as_float(v[c * 8 + 2 * e + 1])), sl2x2, nmx2), a0, a1);
+          float p0, p1;
+          if (((c * 4 + e) & 7) < kPolyOf8) {
+            poly_exp2_pair(a0, a1, p0, p1);
+          } else {
+            p0 = fast_exp2(a0);
+            p1 = fast_exp2(a1);
+          }
           ph[e] = __floats2half2_rn(p0, p1);
           if (!p.sum_in_v) {
             const float2 back = __half22float2(ph[e]);

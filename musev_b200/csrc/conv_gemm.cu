@@ -19,7 +19,7 @@
 
 namespace mvb {
 
-static constexpr int kStages = 4;
+static constexpr int kMaxStages = 8;   // ring depth is chosen per launch: as many (16 KB A + block_n x 128 B) stages as fit
 static constexpr int kBlockM = 128;
 static constexpr int kBlockK = 64;
 static constexpr int kMaxBlockN = 256;
@@ -28,7 +28,8 @@ static constexpr int kBBytes = kMaxBlockN * kBlockK * 2;     // 32 KB
 static constexpr int kStageBytes = kABytes + kBBytes;
 static constexpr int kStagingBufBytes = 128 * 64;               // 128 rows x 32 fp16 output columns
 static constexpr int kStagingBytes = 4 * kStagingBufBytes;       // 2 column-halves x double buffer
-static constexpr int kSmemBytes = kStages * kStageBytes + kStagingBytes + 1024 /*align*/ + 256 /*barriers*/;
+static constexpr int kRingBytes = 4 * kStageBytes;            // 192 KB of operand ring, split into nstages stages
+static constexpr int kSmemBytes = kRingBytes + kStagingBytes + 1024 /*align*/ + 256 /*barriers*/;
 
 __device__ __forceinline__ float gelu_erf(float x) { return 0.5f * x * (1.f + erff(x * 0.70710678118654752440f)); }
 __device__ __forceinline__ float silu(float x) { return x / (1.f + __expf(-x)); }
@@ -49,6 +50,31 @@ __device__ __forceinline__ float gelu_fast(float x) {
   return 0.5f * x * (1.f + erf_v);
 }
 
+// value * gelu_erf(gate) for two columns at once. With w = 0.5 |x| poly(t) exp(-x^2/2) >= 0 (A&S 7.1.26),
+// gelu(x) = max(x, 0) - w for either sign of x.
+__device__ __forceinline__ F2 geglu2(F2 val, F2 gate) {
+  float g0, g1;
+  f2_get(gate, g0, g1);
+  const F2 ax = f2_make(fabsf(g0), fabsf(g1));
+  const F2 z = f2_mul(ax, f2_make(0.70710678118654752440f, 0.70710678118654752440f));
+  float d0, d1;
+  f2_get(f2_fma(z, f2_make(0.3275911f, 0.3275911f), f2_make(1.f, 1.f)), d0, d1);
+  const F2 t = f2_make(__frcp_rn(d0), __frcp_rn(d1));
+  F2 poly = f2_fma(t, f2_make(1.061405429f, 1.061405429f), f2_make(-1.453152027f, -1.453152027f));
+  poly = f2_fma(poly, t, f2_make(1.421413741f, 1.421413741f));
+  poly = f2_fma(poly, t, f2_make(-0.284496736f, -0.284496736f));
+  poly = f2_fma(poly, t, f2_make(0.254829592f, 0.254829592f));
+  poly = f2_mul(poly, t);
+  float a0, a1;
+  f2_get(f2_mul(f2_mul(z, z), f2_make(-1.4426950408889634f, -1.4426950408889634f)), a0, a1);
+  float e0, e1;
+  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(e0) : "f"(a0));
+  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(e1) : "f"(a1));
+  const F2 w = f2_mul(f2_mul(ax, f2_make(-0.5f, -0.5f)), f2_mul(poly, f2_make(e0, e1)));   // -w
+  const F2 gelu = f2_add(f2_make(fmaxf(g0, 0.f), fmaxf(g1, 0.f)), w);
+  return f2_mul(val, gelu);
+}
+
 __global__ void __launch_bounds__(384, 1)
 conv_gemm_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__ CUtensorMap tmA1,
                  const __grid_constant__ CUtensorMap tmA2, const __grid_constant__ CUtensorMap tmA3,
@@ -56,13 +82,15 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant
                  const __grid_constant__ ConvGemmParams p) {
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
-  uint8_t* staging = smem + kStages * kStageBytes;
+  uint8_t* staging = smem + kRingBytes;
   uint64_t* bars = reinterpret_cast<uint64_t*>(staging + kStagingBytes);
-  uint64_t* full = bars;                    // [kStages]
-  uint64_t* empty = bars + kStages;         // [kStages]
-  uint64_t* tfull = bars + 2 * kStages;     // [2]
-  uint64_t* tempty = bars + 2 * kStages + 2;// [2]
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * kStages + 4);
+  uint64_t* full = bars;                       // [kMaxStages]
+  uint64_t* empty = bars + kMaxStages;         // [kMaxStages]
+  uint64_t* tfull = bars + 2 * kMaxStages;     // [2]
+  uint64_t* tempty = bars + 2 * kMaxStages + 2;// [2]
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * kMaxStages + 4);
+  const int nstages = p.nstages;
+  const int stage_bytes = p.stage_bytes;
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
@@ -76,7 +104,7 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant
     tma_prefetch_desc(&tmC);
   }
   if (warp == 1 && lane == 0) {
-    for (int s = 0; s < kStages; ++s) {
+    for (int s = 0; s < kMaxStages; ++s) {
       mbar_init(&full[s], 1);
       mbar_init(&empty[s], 1);
     }
@@ -116,7 +144,7 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant
           const int tap = kb / kb_per_tap;
           const int cb = kb - tap * kb_per_tap;
           mbar_wait(&empty[stage], phase ^ 1);
-          uint8_t* sa = smem + stage * kStageBytes;
+          uint8_t* sa = smem + stage * stage_bytes;
           uint8_t* sb = sa + kABytes;
           mbar_expect_tx(&full[stage], stage_tx);
           const int src = p.tap_src[tap] + (cb < p.kb0 ? 0 : 1);
@@ -124,7 +152,7 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant
           const CUtensorMap* tm = src == 0 ? &tmA0 : (src == 1 ? &tmA1 : (src == 2 ? &tmA2 : &tmA3));
           tma_load_4d(sa, tm, &full[stage], c0, w0 + p.dx[tap], h0 + p.dy[tap], n0);
           tma_load_2d(sb, &tmB, &full[stage], kb * kBlockK, nt * p.block_n);
-          if (++stage == kStages) { stage = 0; phase ^= 1; }
+          if (++stage == nstages) { stage = 0; phase ^= 1; }
         }
       }
     }
@@ -142,7 +170,7 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant
         for (int kb = 0; kb < num_kb; ++kb) {
           mbar_wait(&full[stage], phase);
           tc_fence_after();
-          const uint32_t sa = smem_u32(smem + stage * kStageBytes);
+          const uint32_t sa = smem_u32(smem + stage * stage_bytes);
           const uint32_t sb = sa + kABytes;
           const uint64_t da = make_desc_k_sw128(sa);
           const uint64_t db = make_desc_k_sw128(sb);
@@ -152,7 +180,7 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant
             umma_f16_ss(d_tmem, da + (uint64_t)(k * 2), db + (uint64_t)(k * 2), idesc, (kb | k) != 0);
           }
           umma_commit(&empty[stage]);
-          if (++stage == kStages) { stage = 0; phase ^= 1; }
+          if (++stage == nstages) { stage = 0; phase ^= 1; }
         }
         umma_commit(&tfull[as]);
         if (++as == 2) { as = 0; aphase ^= 1; }
@@ -216,10 +244,17 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant
             const uint32_t* v = hsel ? vb : va;
             const int nb = nbase + hsel * 32;
 #pragma unroll
-            for (int j = 0; j < 16; ++j) {
-              float val = __uint_as_float(v[j]), gate = __uint_as_float(v[16 + j]);
-              if (p.bias) { val += __ldg(p.bias + nb + j); gate += __ldg(p.bias + nb + 16 + j); }
-              f[hsel * 16 + j] = val * gelu_fast(gate);
+            for (int j4 = 0; j4 < 4; ++j4) {
+              // bias of 4 value columns and their 4 gate columns (nb is a multiple of 32: 16-byte aligned float4)
+              const float4 bv = p.bias ? __ldg(reinterpret_cast<const float4*>(p.bias + nb) + j4) : make_float4(0, 0, 0, 0);
+              const float4 bg = p.bias ? __ldg(reinterpret_cast<const float4*>(p.bias + nb + 16) + j4) : make_float4(0, 0, 0, 0);
+              const int j = j4 * 4;
+              const F2 v01 = f2_add(f2_make(__uint_as_float(v[j]), __uint_as_float(v[j + 1])), f2_make(bv.x, bv.y));
+              const F2 v23 = f2_add(f2_make(__uint_as_float(v[j + 2]), __uint_as_float(v[j + 3])), f2_make(bv.z, bv.w));
+              const F2 g01 = f2_add(f2_make(__uint_as_float(v[16 + j]), __uint_as_float(v[16 + j + 1])), f2_make(bg.x, bg.y));
+              const F2 g23 = f2_add(f2_make(__uint_as_float(v[16 + j + 2]), __uint_as_float(v[16 + j + 3])), f2_make(bg.z, bg.w));
+              f2_get(geglu2(v01, g01), f[hsel * 16 + j], f[hsel * 16 + j + 1]);
+              f2_get(geglu2(v23, g23), f[hsel * 16 + j + 2], f[hsel * 16 + j + 3]);
             }
           }
         } else {
@@ -407,6 +442,11 @@ static cudaError_t launch_common(cudaStream_t stream, const CUtensorMap* maps, i
   const long long tiles_m = (long long)p.tiles_w * p.tiles_h * p.tiles_n;
   p.block_n = pick_block_n(p.N, ep.geglu, tiles_m, num_sms);
   p.tiles_nn = ceil_div(p.N, p.block_n);
+  p.stage_bytes = kABytes + ((p.block_n * kBlockK * 2 + 1023) / 1024) * 1024;   // B tile rounded up to the swizzle period
+  p.nstages = kRingBytes / p.stage_bytes;
+  if (p.nstages > kMaxStages) p.nstages = kMaxStages;
+  static const int stage_cap = getenv("MVB_STAGES") ? atoi(getenv("MVB_STAGES")) : 0;   // experiment knob
+  if (stage_cap > 1 && p.nstages > stage_cap) p.nstages = stage_cap;
   p.out = ep.out; p.ldc = ep.ldc; p.bias = ep.bias; p.rowadd = ep.rowadd;
   p.rows_per_group = ep.rows_per_group > 0 ? ep.rows_per_group : 1;
   p.ld_rowadd = ep.ld_rowadd; p.res = ep.res; p.ld_res = ep.ld_res; p.alpha = ep.alpha; p.beta = ep.beta;

@@ -27,6 +27,7 @@ struct ConvGemmParams {
   int kb0, kb1;  // 64-channel blocks contributed by source 0 / source 1 per tap
   int N;         // GEMM N (packed width; with GEGLU the written width is N/2)
   int block_n, tiles_nn;
+  int nstages, stage_bytes;   // operand ring: nstages x (16 KB A tile + block_n x 128 B weight tile)
   // epilogue: v = (acc + bias[n] + rowadd[group(m), n]) * alpha + beta * res[m, n]
   __half* out;
   long long ldc;

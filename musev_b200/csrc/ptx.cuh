@@ -185,6 +185,29 @@ __device__ __forceinline__ void tmem_st16(uint32_t taddr, const uint32_t (&v)[16
       : "memory");
 }
 
+// ---- packed fp32x2 math (FFMA2 / FMUL2 / FADD2 on sm_100): halves the FMA-pipe instruction count of the epilogue
+struct F2 { unsigned long long v; };
+__device__ __forceinline__ F2 f2_make(float a, float b) {
+  F2 r;
+  asm("mov.b64 %0, {%1, %2};" : "=l"(r.v) : "f"(a), "f"(b));
+  return r;
+}
+__device__ __forceinline__ void f2_get(F2 x, float& a, float& b) { asm("mov.b64 {%0, %1}, %2;" : "=f"(a), "=f"(b) : "l"(x.v)); }
+__device__ __forceinline__ F2 f2_fma(F2 a, F2 b, F2 c) {
+  F2 r;
+  asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(r.v) : "l"(a.v), "l"(b.v), "l"(c.v));
+  return r;
+}
+__device__ __forceinline__ F2 f2_mul(F2 a, F2 b) {
+  F2 r;
+  asm("mul.rn.f32x2 %0, %1, %2;" : "=l"(r.v) : "l"(a.v), "l"(b.v));
+  return r;
+}
+__device__ __forceinline__ F2 f2_add(F2 a, F2 b) {
+  F2 r;
+  asm("add.rn.f32x2 %0, %1, %2;" : "=l"(r.v) : "l"(a.v), "l"(b.v));
+  return r;
+}
 // Shared-memory matrix descriptor, K-major operand tile stored as rows of 128 bytes (64 fp16) with the
 // 128-byte swizzle TMA writes: 8-row groups are 1024 bytes apart (SBO), LBO unused for swizzled K-major.
 // Field layout: cute/arch/mma_sm100_desc.hpp (SmemDescriptor): start>>4 [0,14), LBO>>4 [16,30),
