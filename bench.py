@@ -148,7 +148,8 @@ def main():
     dev = torch.device("cuda", local)
     import torch.distributed as dist
     if world > 1:
-        dist.init_process_group("nccl", device_id=dev)
+        import datetime
+        dist.init_process_group("nccl", device_id=dev, timeout=datetime.timedelta(seconds=240))
 
     from musev_b200 import _capi
     from musev_b200.flops import unet_forward_flops
@@ -224,12 +225,14 @@ def main():
     # ---- roofline of the dominant kernel (conv/linear tcgen05 GEMM): CUDA events around every launch of one more
     # denoise step on the launching stream (separate pass so the event records do not perturb the timed regions)
     roof = None
+    # every rank runs the pass (the loop contains a collective); only rank 0 reports it
+    barrier()
+    _capi.profile_enable(True)
+    one_step(lat, cond, prompt)
+    prof = _capi.profile_collect()
+    _capi.profile_enable(False)
+    barrier()
     if rank == 0:
-        torch.cuda.synchronize()
-        _capi.profile_enable(True)
-        one_step(lat, cond, prompt)
-        prof = _capi.profile_collect()
-        _capi.profile_enable(False)
         fl = unet_forward_flops(cfg, 2, WINDOW + 1, LAT_H, LAT_W)
         n_fwd = DDIM_STEPS          # one window per rank -> one UNet forward per DDIM step
         gemm_ms, gemm_n = prof["gemm"]["ms"], prof["gemm"]["launches"]

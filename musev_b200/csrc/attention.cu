@@ -133,10 +133,14 @@ attention_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant_
   const uint32_t tmem_O = tmem_base + 128;
 
   if (warp == 0) {
-    if (lane == 0) {
-      mbar_expect_tx(bar_q, (uint32_t)tile_bytes);
-      for (int a = 0; a < p.natoms; ++a)
-        tma_load_2d(sQ + a * kAtomBytes, &tmQ, bar_q, h * p.dp + a * 64, f * p.Nq + q0);
+    // producer: warp-uniform control flow, one elected lane issues the copies
+    {
+      if (elect_one()) {
+        mbar_expect_tx(bar_q, (uint32_t)tile_bytes);
+        for (int a = 0; a < p.natoms; ++a)
+          tma_load_2d(sQ + a * kAtomBytes, &tmQ, bar_q, h * p.dp + a * 64, f * p.Nq + q0);
+      }
+      __syncwarp();
       auto load_k = [&](int j) {
         int seg, k0, valid;
         tile_info(p, j, &seg, &k0, &valid);
@@ -144,9 +148,12 @@ attention_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant_
         const CUtensorMap* mk = seg ? &tmK1 : &tmK0;
         const int ks = j % p.sk;
         mbar_wait(&empty_k[ks], ((j / p.sk) & 1) ^ 1);
-        mbar_expect_tx(&full_k[ks], (uint32_t)tile_bytes);
-        for (int a = 0; a < p.natoms; ++a)
-          tma_load_2d(sK + ks * tile_bytes + a * kAtomBytes, mk, &full_k[ks], h * p.dp + a * 64, (int)row);
+        if (elect_one()) {
+          mbar_expect_tx(&full_k[ks], (uint32_t)tile_bytes);
+          for (int a = 0; a < p.natoms; ++a)
+            tma_load_2d(sK + ks * tile_bytes + a * kAtomBytes, mk, &full_k[ks], h * p.dp + a * 64, (int)row);
+        }
+        __syncwarp();
       };
       load_k(0);
       for (int j = 0; j < ntiles; ++j) {
@@ -157,13 +164,17 @@ attention_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant_
         const CUtensorMap* mv = seg ? &tmV1 : &tmV0;
         const int vs = j % p.sv;
         mbar_wait(&empty_v[vs], ((j / p.sv) & 1) ^ 1);
-        mbar_expect_tx(&full_v[vs], (uint32_t)tile_bytes);
-        for (int a = 0; a < p.natoms; ++a)
-          tma_load_2d(sV + vs * tile_bytes + a * kAtomBytes, mv, &full_v[vs], h * p.dp + a * 64, (int)row);
+        if (elect_one()) {
+          mbar_expect_tx(&full_v[vs], (uint32_t)tile_bytes);
+          for (int a = 0; a < p.natoms; ++a)
+            tma_load_2d(sV + vs * tile_bytes + a * kAtomBytes, mv, &full_v[vs], h * p.dp + a * 64, (int)row);
+        }
+        __syncwarp();
       }
     }
   } else if (warp == 1) {
-    if (lane == 0) {
+    // MMA issue: warp-uniform loop, elected lane issues
+    {
       const uint32_t idesc_s = make_idesc_f16(128, 128, 0, 0);
       const uint32_t idesc_o = make_idesc_f16(128, p.dp, 0, 1);   // B (= V) is MN-major
       const int ksteps = p.dp / 16;
@@ -174,12 +185,15 @@ attention_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant_
         mbar_wait(&full_k[ks], (j / p.sk) & 1);
         tc_fence_after();
         const uint32_t aK = smem_u32(sK + ks * tile_bytes);
-        for (int kk = 0; kk < ksteps; ++kk) {
-          const uint32_t off = (uint32_t)(kk >> 2) * kAtomBytes + (uint32_t)(kk & 3) * 32;
-          umma_f16_ss(tmem_S, make_desc_k_sw128(aQ + off), make_desc_k_sw128(aK + off), idesc_s, kk != 0);
+        if (elect_one()) {
+          for (int kk = 0; kk < ksteps; ++kk) {
+            const uint32_t off = (uint32_t)(kk >> 2) * kAtomBytes + (uint32_t)(kk & 3) * 32;
+            umma_f16_ss(tmem_S, make_desc_k_sw128(aQ + off), make_desc_k_sw128(aK + off), idesc_s, kk != 0);
+          }
+          umma_commit(&empty_k[ks]);   // K stage free once S_j is done
+          umma_commit(bar_s);
         }
-        umma_commit(&empty_k[ks]);   // K stage free once S_j is done
-        umma_commit(bar_s);
+        __syncwarp();
       };
       issue_s(0);
       for (int j = 0; j < ntiles; ++j) {
@@ -194,14 +208,18 @@ attention_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant_
         tc_fence_after();
         const uint32_t aP = smem_u32(sP);
         const uint32_t aV = smem_u32(sV + vs * tile_bytes);
-        for (int k16 = 0; k16 < 8; ++k16) {
-          const uint32_t offp = (uint32_t)(k16 >> 2) * kAtomBytes + (uint32_t)(k16 & 3) * 32;
-          umma_f16_ss(tmem_O, make_desc_k_sw128(aP + offp), make_desc_mn_sw128(aV + (uint32_t)k16 * 2048, kAtomBytes),
-                      idesc_o, (j | k16) != 0);
+        if (elect_one()) {
+#pragma unroll
+          for (int k16 = 0; k16 < 8; ++k16) {
+            const uint32_t offp = (uint32_t)(k16 >> 2) * kAtomBytes + (uint32_t)(k16 & 3) * 32;
+            umma_f16_ss(tmem_O, make_desc_k_sw128(aP + offp), make_desc_mn_sw128(aV + (uint32_t)k16 * 2048, kAtomBytes),
+                        idesc_o, (j | k16) != 0);
+          }
+          umma_commit(&empty_v[vs]);
+          umma_commit(bar_pv);
+          if (j == ntiles - 1) umma_commit(bar_o);
         }
-        umma_commit(&empty_v[vs]);
-        umma_commit(bar_pv);
-        if (j == ntiles - 1) umma_commit(bar_o);
+        __syncwarp();
       }
     }
   } else {

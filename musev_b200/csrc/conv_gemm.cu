@@ -75,10 +75,18 @@ __device__ __forceinline__ F2 geglu2(F2 val, F2 gate) {
   return f2_mul(val, gelu);
 }
 
+// kTwoCta: the kernel runs as CTA pairs (cluster of 2, tcgen05 cta_group::2): one 256 x block_n tile per pair, each CTA
+// stages its own 128 A rows and HALF of the weight tile, the leader issues M=256 MMAs that read both halves. This cuts
+// the L2->SM operand traffic per FLOP (the measured bound of the 1-CTA kernel, profiles/r01_ncu_full_summary.txt) and
+// halves the MMA issue count.
+struct AMaps {
+  CUtensorMap m[4];   // activation views: [0] source 0, [1] skip-concat source / stride-2 phases 1..3
+};
+
+template <bool kTwoCta>
 __global__ void __launch_bounds__(384, 1)
-conv_gemm_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__ CUtensorMap tmA1,
-                 const __grid_constant__ CUtensorMap tmA2, const __grid_constant__ CUtensorMap tmA3,
-                 const __grid_constant__ CUtensorMap tmB, const __grid_constant__ CUtensorMap tmC,
+conv_gemm_kernel(const __grid_constant__ AMaps tmA, const __grid_constant__ CUtensorMap tmB,
+                 const __grid_constant__ CUtensorMap tmC,
                  const __grid_constant__ ConvGemmParams p) {
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
@@ -96,10 +104,10 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant
   const int lane = threadIdx.x & 31;
 
   if (warp == 0 && lane == 0) {
-    tma_prefetch_desc(&tmA0);
-    tma_prefetch_desc(&tmA1);
-    tma_prefetch_desc(&tmA2);
-    tma_prefetch_desc(&tmA3);
+    tma_prefetch_desc(&tmA.m[0]);
+    tma_prefetch_desc(&tmA.m[1]);
+    tma_prefetch_desc(&tmA.m[2]);
+    tma_prefetch_desc(&tmA.m[3]);
     tma_prefetch_desc(&tmB);
     tma_prefetch_desc(&tmC);
   }
@@ -110,79 +118,110 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant
     }
     for (int s = 0; s < 2; ++s) {
       mbar_init(&tfull[s], 1);
-      mbar_init(&tempty[s], 8);
+      mbar_init(&tempty[s], kTwoCta ? 16 : 8);   // every epilogue warp of the pair reports to the leader
     }
     fence_barrier_init();
   }
   if (warp == 2) {
-    tmem_alloc(tmem_slot, 512);
-    tmem_relinquish();
+    if (kTwoCta) { tmem_alloc_2sm(tmem_slot, 512); tmem_relinquish_2sm(); }
+    else { tmem_alloc(tmem_slot, 512); tmem_relinquish(); }
   }
   tc_fence_before();
-  __syncthreads();
+  if (kTwoCta) cluster_sync_all(); else __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
 
   const int kb_per_tap = p.kb0 + p.kb1;
   const int num_kb = p.ntaps * kb_per_tap;
   const int tiles_m = p.tiles_w * p.tiles_h * p.tiles_n;
-  const int num_tiles = tiles_m * p.tiles_nn;
-  const uint32_t stage_tx = kABytes + (uint32_t)p.block_n * kBlockK * 2;
+  // work units: a unit is one tile (1-CTA) or a pair of vertically adjacent tiles (2-CTA), n fastest
+  const uint32_t crank = kTwoCta ? cluster_ctarank() : 0u;
+  const int unit0 = kTwoCta ? (int)(blockIdx.x >> 1) : (int)blockIdx.x;
+  const int unit_stride = kTwoCta ? (int)(gridDim.x >> 1) : (int)gridDim.x;
+  const int num_units = (kTwoCta ? (tiles_m + 1) / 2 : tiles_m) * p.tiles_nn;
+  const int b_rows = kTwoCta ? p.block_n / 2 : p.block_n;      // weight rows staged by this CTA
+  const uint32_t stage_tx = kABytes + (uint32_t)b_rows * kBlockK * 2;
 
   if (warp == 0) {
-    if (lane == 0) {
+    // TMA producer: warp-uniform loop, one elected lane issues the copies of a stage
+    {
       int stage = 0;
       uint32_t phase = 0;
-      for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
-        const int nt = tile % p.tiles_nn;
-        const int mt = tile / p.tiles_nn;
+      for (int unit = unit0; unit < num_units; unit += unit_stride) {
+        const int nt = unit % p.tiles_nn;
+        const int mt = kTwoCta ? 2 * (unit / p.tiles_nn) + (int)crank : unit / p.tiles_nn;
         const int tw = mt % p.tiles_w;
         const int th = (mt / p.tiles_w) % p.tiles_h;
-        const int tn = mt / (p.tiles_w * p.tiles_h);
+        const int tn = mt / (p.tiles_w * p.tiles_h);   // may run past the last frame in the odd tail of a pair: TMA zero-fills
         const int w0 = tw * p.bw, h0 = th * p.bh, n0 = tn * p.bn;
-        for (int kb = 0; kb < num_kb; ++kb) {
-          const int tap = kb / kb_per_tap;
-          const int cb = kb - tap * kb_per_tap;
-          mbar_wait(&empty[stage], phase ^ 1);
-          uint8_t* sa = smem + stage * stage_bytes;
-          uint8_t* sb = sa + kABytes;
-          mbar_expect_tx(&full[stage], stage_tx);
-          const int src = p.tap_src[tap] + (cb < p.kb0 ? 0 : 1);
-          const int c0 = (cb < p.kb0 ? cb : cb - p.kb0) * kBlockK;
-          const CUtensorMap* tm = src == 0 ? &tmA0 : (src == 1 ? &tmA1 : (src == 2 ? &tmA2 : &tmA3));
-          tma_load_4d(sa, tm, &full[stage], c0, w0 + p.dx[tap], h0 + p.dy[tap], n0);
-          tma_load_2d(sb, &tmB, &full[stage], kb * kBlockK, nt * p.block_n);
-          if (++stage == nstages) { stage = 0; phase ^= 1; }
+        int kcol = 0;                                   // K coordinate of the weight tile
+        const int ncoord = nt * p.block_n + (kTwoCta ? (int)crank * b_rows : 0);
+        for (int tap = 0; tap < p.ntaps; ++tap) {
+          const int xw = w0 + p.dx[tap], yh = h0 + p.dy[tap];
+          const int src0 = p.tap_src[tap];
+          for (int cb = 0; cb < kb_per_tap; ++cb, kcol += kBlockK) {
+            const bool first = cb < p.kb0;
+            const int src = src0 + (first ? 0 : 1);
+            const int c0 = (first ? cb : cb - p.kb0) * kBlockK;
+            const CUtensorMap* tm = &tmA.m[src];
+            mbar_wait(&empty[stage], phase ^ 1);
+            if (elect_one()) {
+              uint8_t* sa = smem + stage * stage_bytes;
+              uint8_t* sb = sa + kABytes;
+              if (kTwoCta) {
+                // both CTAs' copies complete on the LEADER's barrier, which expects the bytes of the whole pair
+                if (crank == 0) mbar_expect_tx(&full[stage], 2 * stage_tx);
+                tma_load_4d_2sm(sa, tm, &full[stage], c0, xw, yh, n0);
+                tma_load_2d_2sm(sb, &tmB, &full[stage], kcol, ncoord);
+              } else {
+                mbar_expect_tx(&full[stage], stage_tx);
+                tma_load_4d(sa, tm, &full[stage], c0, xw, yh, n0);
+                tma_load_2d(sb, &tmB, &full[stage], kcol, ncoord);
+              }
+            }
+            __syncwarp();
+            if (++stage == nstages) { stage = 0; phase ^= 1; }
+          }
         }
       }
     }
   } else if (warp == 1) {
-    if (lane == 0) {
-      const uint32_t idesc = make_idesc_f16(kBlockM, p.block_n, 0, 0);
+    // MMA issue: the whole warp walks the loop (warp-uniform control flow keeps the operands in uniform registers and
+    // avoids the per-instruction lane-election loops a divergent single-thread region needs); one elected lane issues.
+    if (crank == 0) {
+      const uint32_t idesc = make_idesc_f16(kTwoCta ? 2 * kBlockM : kBlockM, p.block_n, 0, 0);
+      const uint64_t desc0_a = make_desc_k_sw128(smem_u32(smem));
+      const uint64_t desc0_b = make_desc_k_sw128(smem_u32(smem) + kABytes);
+      const uint32_t stage_step = (uint32_t)stage_bytes >> 4;     // descriptor address field counts 16-byte units
       int stage = 0;
       uint32_t phase = 0;
       int as = 0;
       uint32_t aphase = 0;
-      for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+      for (int unit = unit0; unit < num_units; unit += unit_stride) {
         mbar_wait(&tempty[as], aphase ^ 1);
         tc_fence_after();
         const uint32_t d_tmem = tmem_base + (uint32_t)as * kMaxBlockN;
         for (int kb = 0; kb < num_kb; ++kb) {
           mbar_wait(&full[stage], phase);
           tc_fence_after();
-          const uint32_t sa = smem_u32(smem + stage * stage_bytes);
-          const uint32_t sb = sa + kABytes;
-          const uint64_t da = make_desc_k_sw128(sa);
-          const uint64_t db = make_desc_k_sw128(sb);
+          const uint64_t da = desc0_a + (uint64_t)((uint32_t)stage * stage_step);
+          const uint64_t db = desc0_b + (uint64_t)((uint32_t)stage * stage_step);
+          if (elect_one()) {
 #pragma unroll
-          for (int k = 0; k < kBlockK / 16; ++k) {
-            // advance 16 K-elements = 32 bytes inside the 128-byte swizzle atom: +2 in the (addr >> 4) field
-            umma_f16_ss(d_tmem, da + (uint64_t)(k * 2), db + (uint64_t)(k * 2), idesc, (kb | k) != 0);
+            for (int k = 0; k < kBlockK / 16; ++k) {
+              // advance 16 K-elements = 32 bytes inside the 128-byte swizzle atom: +2 in the (addr >> 4) field
+              if (kTwoCta) umma_f16_ss_2sm(d_tmem, da + (uint64_t)(k * 2), db + (uint64_t)(k * 2), idesc, (kb | k) != 0);
+              else umma_f16_ss(d_tmem, da + (uint64_t)(k * 2), db + (uint64_t)(k * 2), idesc, (kb | k) != 0);
+            }
+            if (kTwoCta) umma_commit_2sm(&empty[stage], 3); else umma_commit(&empty[stage]);
           }
-          umma_commit(&empty[stage]);
+          __syncwarp();
           if (++stage == nstages) { stage = 0; phase ^= 1; }
         }
-        umma_commit(&tfull[as]);
+        if (elect_one()) {
+          if (kTwoCta) umma_commit_2sm(&tfull[as], 3); else umma_commit(&tfull[as]);
+        }
+        __syncwarp();
         if (++as == 2) { as = 0; aphase ^= 1; }
       }
     }
@@ -199,9 +238,9 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant
     const bool issuer = (q == 0) && (lane == 0);
     const int acc_step = p.geglu ? 64 : 32;             // accumulator columns consumed per 32 output columns
     uint32_t chunk_iter = 0;
-    for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
-      const int nt = tile % p.tiles_nn;
-      const int mt = tile / p.tiles_nn;
+    for (int unit = unit0; unit < num_units; unit += unit_stride) {
+      const int nt = unit % p.tiles_nn;
+      const int mt = kTwoCta ? 2 * (unit / p.tiles_nn) + (int)crank : unit / p.tiles_nn;
       const int tw = mt % p.tiles_w;
       const int th = (mt / p.tiles_w) % p.tiles_h;
       const int tn = mt / (p.tiles_w * p.tiles_h);
@@ -337,15 +376,19 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant
       }
       tc_fence_before();
       __syncwarp();
-      if (lane == 0) mbar_arrive(&tempty[as]);
+      if (lane == 0) {
+        if (kTwoCta) mbar_arrive_remote(&tempty[as], 0); else mbar_arrive(&tempty[as]);
+      }
       if (++as == 2) { as = 0; aphase ^= 1; }
     }
     if (issuer) tma_store_wait_all();   // smem must stay valid until the last bulk store has read it
   }
 
   tc_fence_before();
-  __syncthreads();
-  if (warp == 2) tmem_dealloc(tmem_base, 512);
+  if (kTwoCta) cluster_sync_all(); else __syncthreads();
+  if (warp == 2) {
+    if (kTwoCta) tmem_dealloc_2sm(tmem_base, 512); else tmem_dealloc(tmem_base, 512);
+  }
 }
 
 // ------------------------------------------------------------------ host side
@@ -435,7 +478,9 @@ static cudaError_t launch_common(cudaStream_t stream, const CUtensorMap* maps, i
                                  const __half* wt, long long ktot, const Epilogue& ep, int num_sms, const char** err) {
   static bool attr_set = false;
   if (!attr_set) {
-    cudaError_t e = cudaFuncSetAttribute(conv_gemm_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemBytes);
+    cudaError_t e = cudaFuncSetAttribute(conv_gemm_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemBytes);
+    if (e == cudaSuccess)
+      e = cudaFuncSetAttribute(conv_gemm_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemBytes);
     if (e != cudaSuccess) { *err = "cudaFuncSetAttribute(conv_gemm_kernel)"; return e; }
     attr_set = true;
   }
@@ -452,8 +497,17 @@ static cudaError_t launch_common(cudaStream_t stream, const CUtensorMap* maps, i
   p.ld_rowadd = ep.ld_rowadd; p.res = ep.res; p.ld_res = ep.ld_res; p.alpha = ep.alpha; p.beta = ep.beta;
   p.geglu = ep.geglu; p.act = ep.act; p.out_f32 = ep.out_f32;
   if (ep.out_f32 && (ep.geglu || ep.res)) { *err = "conv_gemm: fp32 output excludes geglu/residual"; return cudaErrorInvalidValue; }
+  // CTA pairs when there is enough work for all 74 pairs (env MVB_TWOCTA=0/1 forces the choice for experiments)
+  static const int twocta_env = getenv("MVB_TWOCTA") ? atoi(getenv("MVB_TWOCTA")) : -1;
+  const long long pair_units = ((tiles_m + 1) / 2) * p.tiles_nn;
+  // pairs pay off when the mainloop dominates (K >= 1280: +5..9 % measured); short-K GEMMs are epilogue-bound and
+  // lose ~15 % to the pair-wide accumulator hand-off
+  bool two_cta = tiles_m >= 2 && pair_units >= (num_sms / 2) && (num_sms % 2 == 0) && ktot >= 1280;
+  if (twocta_env == 0) two_cta = false;
+  if (twocta_env == 1 && tiles_m >= 2 && (num_sms % 2 == 0)) two_cta = true;
   CUtensorMap tmB;
-  if (!encode_map_2d(&tmB, wt, (uint64_t)ktot, (uint64_t)p.N, (uint64_t)ktot, 64u, (uint32_t)p.block_n)) {
+  if (!encode_map_2d(&tmB, wt, (uint64_t)ktot, (uint64_t)p.N, (uint64_t)ktot, 64u,
+                     (uint32_t)(two_cta ? p.block_n / 2 : p.block_n))) {
     *err = "cuTensorMapEncodeTiled(B) failed";
     return cudaErrorInvalidValue;
   }
@@ -471,18 +525,33 @@ static cudaError_t launch_common(cudaStream_t stream, const CUtensorMap* maps, i
     }
   }
   const long long num_tiles = tiles_m * p.tiles_nn;
-  const int grid = (int)(num_tiles < num_sms ? num_tiles : num_sms);
+  int grid = (int)(num_tiles < num_sms ? num_tiles : num_sms);
+  if (two_cta) grid = (int)(2 * (pair_units < num_sms / 2 ? pair_units : num_sms / 2));
   static const bool trace = getenv("MVB_TRACE") != nullptr;
   if (trace)
-    fprintf(stderr, "MVB_TRACE gemm M=%lld N=%d K=%lld taps=%d block_n=%d tiles=%lld geglu=%d res=%d f32=%d\n",
-            (long long)p.W * p.H * p.NF, p.N, ktot, p.ntaps, p.block_n, num_tiles, p.geglu, p.res != nullptr, p.out_f32);
-  const CUtensorMap& m0 = maps[0];
-  const CUtensorMap& m1 = maps[nmaps > 1 ? 1 : 0];
-  const CUtensorMap& m2 = maps[nmaps > 2 ? 2 : 0];
-  const CUtensorMap& m3 = maps[nmaps > 3 ? 3 : 0];
+    fprintf(stderr, "MVB_TRACE gemm M=%lld N=%d K=%lld taps=%d block_n=%d tiles=%lld geglu=%d res=%d f32=%d cta2=%d\n",
+            (long long)p.W * p.H * p.NF, p.N, ktot, p.ntaps, p.block_n, num_tiles, p.geglu, p.res != nullptr, p.out_f32,
+            (int)two_cta);
+  AMaps am;
+  for (int i = 0; i < 4; ++i) am.m[i] = maps[i < nmaps ? i : 0];
   ProfScope prof(stream, KC_GEMM);
-  conv_gemm_kernel<<<grid, 384, kSmemBytes, stream>>>(m0, m1, m2, m3, tmB, tmC, p);
-  cudaError_t e = cudaGetLastError();
+  cudaError_t e;
+  if (two_cta) {
+    cudaLaunchConfig_t cfg{};
+    cfg.gridDim = dim3(grid);
+    cfg.blockDim = dim3(384);
+    cfg.dynamicSmemBytes = kSmemBytes;
+    cfg.stream = stream;
+    cudaLaunchAttribute at[1];
+    at[0].id = cudaLaunchAttributeClusterDimension;
+    at[0].val.clusterDim.x = 2; at[0].val.clusterDim.y = 1; at[0].val.clusterDim.z = 1;
+    cfg.attrs = at;
+    cfg.numAttrs = 1;
+    e = cudaLaunchKernelEx(&cfg, conv_gemm_kernel<true>, am, tmB, tmC, p);
+  } else {
+    conv_gemm_kernel<false><<<grid, 384, kSmemBytes, stream>>>(am, tmB, tmC, p);
+    e = cudaGetLastError();
+  }
   if (e != cudaSuccess) *err = "conv_gemm_kernel launch";
   return e;
 }

@@ -33,7 +33,9 @@ def _pad_heads(x, heads, d, dp, ones=False):
     return o.view(x.shape[0], heads * dp)
 
 
-@pytest.mark.parametrize("M,K,N", [(128, 64, 64), (100, 64, 48), (1000, 320, 320), (4096, 1280, 640), (2, 320, 1280)])
+# the last two shapes have >= 74 tile pairs: they run the CTA-pair (cta_group::2) variant, one with an odd tile count
+@pytest.mark.parametrize("M,K,N", [(128, 64, 64), (100, 64, 48), (1000, 320, 320), (4096, 1280, 640), (2, 320, 1280),
+                                   (40000, 128, 320), (149 * 128 + 37, 192, 64)])
 def test_linear(ops, M, K, N):
     torch.manual_seed(0)
     a = torch.randn(1, 1, M, K, device=dev).half()
@@ -45,7 +47,8 @@ def test_linear(ops, M, K, N):
 
 
 @pytest.mark.parametrize("NF,H,W,C,N,C1", [(2, 16, 16, 64, 64, 0), (3, 8, 8, 128, 320, 0), (2, 32, 32, 640, 640, 320),
-                                           (5, 4, 4, 64, 64, 0), (2, 24, 16, 64, 128, 0)])
+                                           (5, 4, 4, 64, 64, 0), (2, 24, 16, 64, 128, 0), (34, 32, 32, 64, 64, 0),
+                                           (9, 32, 32, 64, 160, 64)])
 def test_conv3x3(ops, NF, H, W, C, N, C1):
     torch.manual_seed(1)
     x = torch.randn(NF, H, W, C, device=dev).half()
