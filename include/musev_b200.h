@@ -94,7 +94,7 @@ int mvb_op_temporal_attention(const void* qkv, int ld, int B, int T, int HW, int
 
 /* GroupNorm (+SiLU) on channels-last fp16 [NF, HW, C0 (+C1)] (F.group_norm at diffusers models/resnet.py:641,662;
  * musev/models/resnet.py:57-74; temporal_transformer.py:117). frames_per_stat = 1: per-frame statistics;
- * = T: the reference's 5-D GroupNorm over (c/g, t, h, w). `scratch` >= NF*17*groups*2 floats. */
+ * = T: the reference's 5-D GroupNorm over (c/g, t, h, w). `scratch` >= NF*65*groups*2 floats. */
 int mvb_op_groupnorm(const void* x0, int c0, const void* x1, int c1, int NF, int HW, int groups, int frames_per_stat,
                      float eps, const float* gamma, const float* beta, int silu, void* y, float* scratch, void* stream);
 

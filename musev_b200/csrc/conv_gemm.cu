@@ -27,8 +27,9 @@ static constexpr int kABytes = kBlockM * kBlockK * 2;        // 16 KB
 static constexpr int kBBytes = kMaxBlockN * kBlockK * 2;     // 32 KB
 static constexpr int kStageBytes = kABytes + kBBytes;
 static constexpr int kStagingBufBytes = 128 * 64;               // 128 rows x 32 fp16 output columns
-static constexpr int kStagingBytes = 4 * kStagingBufBytes;       // 2 column-halves x double buffer
-static constexpr int kRingBytes = 4 * kStageBytes;            // 192 KB of operand ring, split into nstages stages
+static constexpr int kStagingDepth = 4;                         // staging buffers per column half (3 TMA stores in flight)
+static constexpr int kStagingBytes = 2 * kStagingDepth * kStagingBufBytes;
+static constexpr int kRingBytes = 160 * 1024;                 // operand ring, split into nstages stages
 static constexpr int kSmemBytes = kRingBytes + kStagingBytes + 1024 /*align*/ + 256 /*barriers*/;
 
 __device__ __forceinline__ float gelu_erf(float x) { return 0.5f * x * (1.f + erff(x * 0.70710678118654752440f)); }
@@ -343,9 +344,10 @@ conv_gemm_kernel(const __grid_constant__ AMaps tmA, const __grid_constant__ CUte
           }
         } else {
           // finish in fp32, round to fp16, stage, store
-          uint8_t* buf = staging + (half * 2 + (chunk_iter & 1)) * kStagingBufBytes;
-          if (issuer) tma_store_wait_read<1>();            // the store that last read this buffer has drained
-          named_bar_sync(1 + half, 128);
+          // staging ring of kStagingDepth buffers, ONE barrier per chunk: chunk i is written while stores i-1..i-3 drain
+          // (a TMA store takes ~1 us to release its smem source); before barrier i the issuer makes sure store
+          // i-(depth-1) is done, so after the barrier everybody knows the buffer of chunk i+1 is free
+          uint8_t* buf = staging + (half * kStagingDepth + (chunk_iter % kStagingDepth)) * kStagingBufBytes;
 #pragma unroll
           for (int g = 0; g < 4; ++g) {
             __align__(16) __half o[8];
@@ -363,6 +365,7 @@ conv_gemm_kernel(const __grid_constant__ AMaps tmA, const __grid_constant__ CUte
             *reinterpret_cast<uint4*>(buf + r * 64 + ((g ^ ((r >> 1) & 3)) << 4)) = *reinterpret_cast<const uint4*>(o);
           }
           fence_proxy_async();
+          if (issuer) tma_store_wait_read<kStagingDepth - 2>();
           named_bar_sync(1 + half, 128);
           if (issuer) {
             const int oc = p.geglu ? nbase / 2 : nbase;

@@ -40,13 +40,28 @@ gn_stats_kernel(const __half* __restrict__ x0, int C0, const __half* __restrict_
       const __half* src = (c < C0) ? x0 + (size_t)f * HW * C0 + c : x1 + (size_t)f * HW * C1 + (c - C0);
       const int ld = (c < C0) ? C0 : C1;
       float s[4] = {0, 0, 0, 0}, q[4] = {0, 0, 0, 0};
-      for (int p = p_begin + r0; p < p_end; p += rows_per_iter) {
+      int p = p_begin + r0;
+      // four independent 16-byte loads in flight per thread
+      for (; p + 3 * rows_per_iter < p_end; p += 4 * rows_per_iter) {
+        Half8 hv[4];
+#pragma unroll
+        for (int u = 0; u < 4; ++u) hv[u] = *reinterpret_cast<const Half8*>(src + (size_t)(p + u * rows_per_iter) * ld);
+#pragma unroll
+        for (int u = 0; u < 4; ++u)
+#pragma unroll
+          for (int j = 0; j < 4; ++j) {
+            const float2 t = __half22float2(hv[u].h[j]);
+            s[j] += t.x + t.y;
+            q[j] = fmaf(t.x, t.x, fmaf(t.y, t.y, q[j]));
+          }
+      }
+      for (; p < p_end; p += rows_per_iter) {
         const Half8 hv = *reinterpret_cast<const Half8*>(src + (size_t)p * ld);
 #pragma unroll
         for (int j = 0; j < 4; ++j) {
           const float2 t = __half22float2(hv.h[j]);
           s[j] += t.x + t.y;
-          q[j] += t.x * t.x + t.y * t.y;
+          q[j] = fmaf(t.x, t.x, fmaf(t.y, t.y, q[j]));
         }
       }
 #pragma unroll
@@ -75,9 +90,9 @@ cudaError_t gn_stats(cudaStream_t s, const __half* x0, int C0, const __half* x1,
   if (!x1) C1 = 0;
   if ((C0 % 8) || (C1 % 8) || (C % G) || ((C / G) % 2)) return cudaErrorInvalidValue;
   const int threads = 256;
-  // enough blocks for ~2 waves, at least ~64 pixels per block
-  int chunks = (2 * 148 + NF - 1) / NF;
-  const int maxc = HW / 64 > 0 ? HW / 64 : 1;
+  // ~8 resident blocks per SM (the kernel is latency-bound below that), at least ~32 pixels per block
+  int chunks = (8 * 148 + NF - 1) / NF;
+  const int maxc = HW / 32 > 0 ? HW / 32 : 1;
   if (chunks > maxc) chunks = maxc;
   if (chunks > kGnMaxChunks) chunks = kGnMaxChunks;
   if (chunks < 1) chunks = 1;

@@ -7,7 +7,7 @@
 
 namespace mvb {
 
-static constexpr int kGnMaxChunks = 16;
+static constexpr int kGnMaxChunks = 64;
 
 // GroupNorm statistics. x0 [NF, HW, C0] (+ optional x1 [NF, HW, C1] = channel concat). Writes per-frame partial
 // (sum, sumsq) per group: part[NF][chunks][G][2] fp32. Returns the number of chunks used through *chunks.

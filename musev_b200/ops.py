@@ -115,7 +115,7 @@ def groupnorm(x0, gamma, beta, groups=32, frames_per_stat=1, eps=1e-5, silu=Fals
     NF, HW, C0 = x0.shape
     C1 = 0 if x1 is None else x1.shape[2]
     y = torch.empty((NF, HW, C0 + C1), dtype=torch.float16, device=x0.device)
-    scratch = torch.empty(NF * 17 * groups * 2, dtype=torch.float32, device=x0.device)
+    scratch = torch.empty(NF * 65 * groups * 2, dtype=torch.float32, device=x0.device)
     _capi.check(_capi.lib().mvb_op_groupnorm(x0.data_ptr(), C0, _ptr(x1), C1, NF, HW, groups, frames_per_stat, eps,
                                              gamma.data_ptr(), beta.data_ptr(), int(silu), y.data_ptr(),
                                              scratch.data_ptr(), _stream()))
