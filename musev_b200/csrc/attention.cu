@@ -40,20 +40,18 @@ struct AttnParams {
 static constexpr int kAtomBytes = 128 * 128;  // 128 rows x 64 fp16
 static constexpr int kPolyOf8 = 3;             // of every 8 column pairs, this many take the FMA-pipe exp2
 
-// 2^x for a pair of arguments on the FMA / ALU pipes (no SFU): round-to-nearest split x = n + f, |f| <= 0.5, degree-4
-// polynomial for 2^f (relative error < 5e-5, an order of magnitude below the fp16 rounding of P), exponent patched in
-// with integer arithmetic. Used for a fixed share of the softmax columns so that the SFU (16 ex2/clk/SM), which bounds
-// this kernel at head dim 40, and the FMA pipe work in parallel.
+// 2^x for a pair of arguments on the FMA / ALU pipes (no SFU): round-to-nearest split x = n + f, |f| <= 0.5, degree-3
+// minimax polynomial for 2^f (relative error < 7.5e-5, well below the 4.9e-4 fp16 rounding of P), exponent patched in
+// with one integer multiply-add. Used for a fixed share of the softmax columns so that the SFU (16 ex2/clk/SM), which
+// bounds this kernel at head dim 40, and the FMA pipe work in parallel.
 __device__ __forceinline__ void poly_exp2_pair(float a0, float a1, float& p0, float& p1) {
   const F2 a = f2_make(fmaxf(a0, -125.f), fmaxf(a1, -125.f));
-  const F2 magic = f2_make(12582912.f, 12582912.f);
-  const F2 t = f2_add(a, magic);
+  const F2 t = f2_add(a, f2_make(12582912.f, 12582912.f));
   const F2 nf = f2_add(t, f2_make(-12582912.f, -12582912.f));
   const F2 f = f2_fma(nf, f2_make(-1.f, -1.f), a);
-  F2 q = f2_fma(f, f2_make(0.00961812911f, 0.00961812911f), f2_make(0.0555041087f, 0.0555041087f));
-  q = f2_fma(q, f, f2_make(0.240226507f, 0.240226507f));
-  q = f2_fma(q, f, f2_make(0.693147181f, 0.693147181f));
-  q = f2_fma(q, f, f2_make(1.f, 1.f));
+  F2 q = f2_fma(f, f2_make(0.0551716648f, 0.0551716648f), f2_make(0.242611125f, 0.242611125f));
+  q = f2_fma(q, f, f2_make(0.693260968f, 0.693260968f));
+  q = f2_fma(q, f, f2_make(0.999928057f, 0.999928057f));
   float q0, q1, t0, t1;
   f2_get(q, q0, q1);
   f2_get(t, t0, t1);
@@ -76,6 +74,7 @@ __device__ __forceinline__ void tile_info(const AttnParams& p, int j, int* seg, 
   }
 }
 
+template <bool kSumInV>
 __global__ void __launch_bounds__(320, 2)
 attention_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUtensorMap tmK0,
                  const __grid_constant__ CUtensorMap tmV0, const __grid_constant__ CUtensorMap tmK1,
@@ -223,24 +222,32 @@ attention_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant_
       }
     }
   } else {
-    // 8 softmax warps: two threads per query row, each owning 64 of the 128 key columns of the tile
+    // 8 softmax warps: two threads per query row, each owning 64 of the 128 key columns of the tile. Warps w and w+4
+    // hold the two halves of the same 32 rows and are the only ones that have to agree on the row max, so each such
+    // pair has its own 64-thread named barrier: the four pairs drift apart and cover each other's stalls.
     const int qd = warp & 3;
     const int ch = (warp - 2) >> 2;                 // column half: keys [64 ch, 64 ch + 64) = P atom `ch`
     const int row = qd * 32 + lane;
     const uint32_t lane_off = (uint32_t)(qd * 32) << 16;
+    const uint32_t a_prow = smem_u32(sP) + (uint32_t)ch * kAtomBytes + (uint32_t)row * 128;
+    const uint32_t rx = (uint32_t)(row & 7) << 4;
+    const uint32_t a_mine = smem_u32(smax) + (uint32_t)(ch * 128 + row) * 4;
+    const uint32_t a_peer = smem_u32(smax) + (uint32_t)((ch ^ 1) * 128 + row) * 4;
+    const uint32_t a_bar_s = smem_u32(bar_s), a_bar_sfree = smem_u32(bar_sfree), a_bar_pv = smem_u32(bar_pv),
+                   a_bar_p = smem_u32(bar_p);
+    const int t0 = (p.nk[0] + 127) / 128;
     float m = -INFINITY, l = 0.f;
     const float sl2 = p.scale_log2;
     for (int j = 0; j < ntiles; ++j) {
-      int seg, k0, valid;
-      tile_info(p, j, &seg, &k0, &valid);
-      mbar_wait(bar_s, j & 1);
+      const int valid = j < t0 ? min(128, p.nk[0] - j * 128) : min(128, p.nk[1] - (j - t0) * 128);
+      mbar_wait_a(a_bar_s, j & 1);
       tc_fence_after();
       uint32_t v[64];
       tmem_ld32(tmem_S + lane_off + ch * 64, *reinterpret_cast<uint32_t(*)[32]>(&v[0]));
       tmem_ld32(tmem_S + lane_off + ch * 64 + 32, *reinterpret_cast<uint32_t(*)[32]>(&v[32]));
       tmem_ld_wait();
       tc_fence_before();
-      mbar_arrive(bar_sfree);            // the tensor core may start S_{j+1} now
+      mbar_arrive_a(a_bar_sfree);        // the tensor core may start S_{j+1} now
       if (valid < 128) {
 #pragma unroll
         for (int i = 0; i < 64; ++i)
@@ -257,15 +264,15 @@ attention_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant_
       float mx = fmaxf(fmaxf(fmaxf(mxs[0], mxs[1]), fmaxf(mxs[2], mxs[3])),
                        fmaxf(fmaxf(mxs[4], mxs[5]), fmaxf(mxs[6], mxs[7])));
       // combine with the partner thread (other column half of the same row) through smem
-      float* xch = smax + (j & 1) * 256;
-      xch[ch * 128 + row] = mx;
-      named_bar_sync(1, 256);
-      mx = fmaxf(mx, xch[(ch ^ 1) * 128 + row]) * sl2;
+      const uint32_t xoff = (uint32_t)(j & 1) * 1024;
+      sts32f(a_mine + xoff, mx);
+      named_bar_sync(1 + qd, 64);
+      mx = fmaxf(mx, lds32f(a_peer + xoff)) * sl2;
       const bool need = mx > m + 8.f;
       float alpha = 1.f;
       if (need) { alpha = fast_exp2(m - mx); m = mx; }
       if (j > 0) {
-        mbar_wait(bar_pv, (j - 1) & 1);  // P buffer free again and O_{j-1} final before it is rescaled
+        mbar_wait_a(a_bar_pv, (j - 1) & 1);  // P buffer free again and O_{j-1} final before it is rescaled
         tc_fence_after();
       }
       if (j > 0 && __any_sync(0xffffffffu, need)) {
@@ -280,51 +287,51 @@ attention_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant_
         }
         tmem_st_wait();
       }
-      l *= alpha;
       const F2 sl2x2 = f2_make(sl2, sl2), nmx2 = f2_make(-m, -m);
       float ls0 = 0.f, ls1 = 0.f;
-      uint8_t* prow = sP + ch * kAtomBytes + row * 128;
 #pragma unroll
       for (int c = 0; c < 8; ++c) {   // 8 chunks of 8 keys = one 16-byte smem store each
-        __align__(16) __half2 ph[4];
+        uint32_t ph[4];
 #pragma unroll
         for (int e = 0; e < 4; ++e) {
+          const int i = c * 4 + e;    // column pair; kPolyOf8 of every 8 pairs, evenly spread, take the FMA-pipe exp2
           float a0, a1;
-          f2_get(f2_fma(f2_make(__uint_as_float(v[c * 8 + 2 * e]), __uint_as_float(v[c * 8 + 2 * e + 1])), sl2x2, nmx2), a0, a1);
+          f2_get(f2_fma(f2_make(__uint_as_float(v[2 * i]), __uint_as_float(v[2 * i + 1])), sl2x2, nmx2), a0, a1);
           float p0, p1;
-          if (((c * 4 + e) & 7) < kPolyOf8) {
+          if (((i * kPolyOf8) & 7) < kPolyOf8) {
             poly_exp2_pair(a0, a1, p0, p1);
           } else {
             p0 = fast_exp2(a0);
             p1 = fast_exp2(a1);
           }
-          ph[e] = __floats2half2_rn(p0, p1);
-          if (!p.sum_in_v) {
-            const float2 back = __half22float2(ph[e]);
+          const __half2 hp = __floats2half2_rn(p0, p1);
+          ph[e] = *reinterpret_cast<const uint32_t*>(&hp);
+          if (!kSumInV) {
+            const float2 back = __half22float2(hp);
             ls0 += back.x; ls1 += back.y;
           }
         }
-        *reinterpret_cast<uint4*>(prow + ((c ^ (row & 7)) << 4)) = *reinterpret_cast<const uint4*>(ph);
+        sts128(a_prow + (((uint32_t)c << 4) ^ rx), ph[0], ph[1], ph[2], ph[3]);
       }
-      l += ls0 + ls1;
+      if (!kSumInV) l = l * alpha + (ls0 + ls1);
       fence_proxy_async();
       tc_fence_before();
-      mbar_arrive(bar_p);
+      mbar_arrive_a(a_bar_p);
     }
     // epilogue
     mbar_wait(bar_o, 0);
     tc_fence_after();
-    if (p.sum_in_v) {
+    if (kSumInV) {
       // the row sum was accumulated by the tensor core: V carries a column of ones at index d
       uint32_t o[16];
       tmem_ld16(tmem_O + lane_off + (p.d / 16) * 16, o);
       tmem_ld_wait();
       l = __uint_as_float(o[p.d % 16 == 8 ? 8 : 0]);
     } else {
-      float* xch = smax + (ntiles & 1) * 256;
-      xch[ch * 128 + row] = l;
-      named_bar_sync(1, 256);
-      l += xch[(ch ^ 1) * 128 + row];
+      const uint32_t xoff = (uint32_t)(ntiles & 1) * 1024;
+      sts32f(a_mine + xoff, l);
+      named_bar_sync(1 + qd, 64);
+      l += lds32f(a_peer + xoff);
     }
     const float inv = p.out_scale / l;
     const int qrow = q0 + row;
@@ -385,7 +392,9 @@ cudaError_t launch_attention(cudaStream_t stream, const AttnArgs& a, const char*
   const int smem = (1 + p.sk + p.sv) * p.natoms * kAtomBytes + 2 * kAtomBytes + 1024 + 128 + 2048;
   static int max_set = 0;
   if (smem > max_set) {
-    cudaError_t e = cudaFuncSetAttribute(attention_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
+    cudaError_t e = cudaFuncSetAttribute(attention_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
+    if (e == cudaSuccess)
+      e = cudaFuncSetAttribute(attention_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
     if (e != cudaSuccess) { *err = "cudaFuncSetAttribute(attention_kernel)"; return e; }
     max_set = 227 * 1024;
   }
@@ -408,7 +417,8 @@ cudaError_t launch_attention(cudaStream_t stream, const AttnArgs& a, const char*
             p.nk[1], a.accumulate);
   dim3 grid((a.Nq + 127) / 128, a.heads, a.NF);
   ProfScope prof(stream, KC_ATTENTION);
-  attention_kernel<<<grid, 320, smem, stream>>>(tq, tk0, tv0, tk1, tv1, p);
+  if (p.sum_in_v) attention_kernel<true><<<grid, 320, smem, stream>>>(tq, tk0, tv0, tk1, tv1, p);
+  else attention_kernel<false><<<grid, 320, smem, stream>>>(tq, tk0, tv0, tk1, tv1, p);
   cudaError_t e = cudaGetLastError();
   if (e != cudaSuccess) *err = "attention_kernel launch";
   return e;

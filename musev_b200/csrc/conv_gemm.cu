@@ -33,7 +33,7 @@ static constexpr int kRingBytes = 160 * 1024;                 // operand ring, s
 static constexpr int kSmemBytes = kRingBytes + kStagingBytes + 1024 /*align*/ + 256 /*barriers*/;
 
 __device__ __forceinline__ float gelu_erf(float x) { return 0.5f * x * (1.f + erff(x * 0.70710678118654752440f)); }
-__device__ __forceinline__ float silu(float x) { return x / (1.f + __expf(-x)); }
+__device__ __forceinline__ float silu(float x) { return __fdividef(x, 1.f + __expf(-x)); }
 // exact-erf GELU (diffusers activations.py:89-102 uses F.gelu default) with erf from Abramowitz-Stegun 7.1.26
 // (|error| < 1.5e-7, far below the fp16 output rounding): one reciprocal, one exp2, a degree-5 polynomial.
 __device__ __forceinline__ float gelu_fast(float x) {

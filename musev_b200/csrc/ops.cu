@@ -8,7 +8,8 @@
 
 namespace mvb {
 
-__device__ __forceinline__ float silu_f(float x) { return x / (1.f + __expf(-x)); }
+// x * sigmoid(x) with the two SFU approximations (ex2, rcp): ~1e-6 relative, five instructions
+__device__ __forceinline__ float silu_f(float x) { return __fdividef(x, 1.f + __expf(-x)); }
 
 struct alignas(16) Half8 {
   __half2 h[4];
@@ -163,6 +164,29 @@ gn_apply_kernel(const __half* __restrict__ x0, int C0, const __half* __restrict_
       be[j] = __ldg(beta + c + j) - sm_gn[g] * ga[j];
     }
   }
+  if (fixed_col) {
+    // the thread walks down its channel vector: no per-element index arithmetic, affine terms in registers
+    const int c = (threadIdx.x % vecs) * 8;
+    const int rstep = blockDim.x / vecs;
+    const __half* src = (c < C0) ? x0 + (size_t)f * HW * C0 + c : x1 + (size_t)f * HW * C1 + (c - C0);
+    const int ld = (c < C0) ? C0 : C1;
+    __half* dst = y + (size_t)f * HW * C + c;
+#pragma unroll 2
+    for (int p = p0 + threadIdx.x / vecs; p < p1; p += rstep) {
+      const Half8 hv = *reinterpret_cast<const Half8*>(src + (size_t)p * ld);
+      Half8 ov;
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        float2 t = __half22float2(hv.h[j]);
+        t.x = fmaf(t.x, ga[2 * j], be[2 * j]);
+        t.y = fmaf(t.y, ga[2 * j + 1], be[2 * j + 1]);
+        if (silu) { t.x = silu_f(t.x); t.y = silu_f(t.y); }
+        ov.h[j] = __floats2half2_rn(t.x, t.y);
+      }
+      *reinterpret_cast<Half8*>(dst + (size_t)p * C) = ov;
+    }
+    return;
+  }
   for (int i = threadIdx.x; i < total; i += blockDim.x) {
     const int p = p0 + i / vecs;
     const int c = (i % vecs) * 8;
@@ -284,10 +308,89 @@ layernorm_kernel(const __half* __restrict__ x, long long M, int C, float eps, co
   }
 }
 
+// C = 40 L (320 / 640 / 1280, the three transformer widths): L lanes share a row, each lane owns 5 vectors of 8
+// channels (vector index = lane_in_row + L i, so a row is read as 5 fully coalesced segments) and a warp streams 32/L
+// rows at a time; gamma / beta sit in smem. Two-pass (centered) variance on the register copy, ~8 instructions per
+// element, which keeps the kernel on the HBM roofline instead of the issue port.
+template <int L>
+__global__ void __launch_bounds__(256)
+layernorm40_kernel(const __half* __restrict__ x, long long M, float eps, const float* __restrict__ gamma,
+                   const float* __restrict__ beta, __half* __restrict__ y) {
+  constexpr int C = 40 * L;
+  constexpr int RPW = 32 / L;   // rows per warp pass
+  __shared__ __align__(16) float sg[C], sb[C];
+  for (int i = threadIdx.x; i < C; i += blockDim.x) { sg[i] = gamma[i]; sb[i] = beta[i]; }
+  __syncthreads();
+  const int lane = threadIdx.x & 31;
+  const int lr = lane % L;          // lane within the row
+  const int rw = lane / L;          // row within the warp pass
+  const long long groups = (M + RPW - 1) / RPW;
+  const long long gstride = (long long)gridDim.x * (blockDim.x / 32);
+  for (long long g = (long long)blockIdx.x * (blockDim.x / 32) + (threadIdx.x >> 5); g < groups; g += gstride) {
+    const long long row = g * RPW + rw;
+    const bool ok = row < M;
+    Half8 hv[5];
+#pragma unroll
+    for (int i = 0; i < 5; ++i)
+      hv[i] = ok ? *reinterpret_cast<const Half8*>(x + row * C + (lr + L * i) * 8) : Half8{};
+    float v[5][8];
+    float s0 = 0.f, s1 = 0.f;
+#pragma unroll
+    for (int i = 0; i < 5; ++i)
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        const float2 t = __half22float2(hv[i].h[j]);
+        v[i][2 * j] = t.x; v[i][2 * j + 1] = t.y;
+        s0 += t.x; s1 += t.y;
+      }
+    float sum = s0 + s1;
+#pragma unroll
+    for (int o = L / 2; o > 0; o >>= 1) sum += __shfl_xor_sync(0xffffffffu, sum, o);
+    const float mean = sum * (1.f / C);
+    float q0 = 0.f, q1 = 0.f;
+#pragma unroll
+    for (int i = 0; i < 5; ++i)
+#pragma unroll
+      for (int j = 0; j < 8; j += 2) {
+        const float d0 = v[i][j] - mean, d1 = v[i][j + 1] - mean;
+        q0 = fmaf(d0, d0, q0); q1 = fmaf(d1, d1, q1);
+      }
+    float q = q0 + q1;
+#pragma unroll
+    for (int o = L / 2; o > 0; o >>= 1) q += __shfl_xor_sync(0xffffffffu, q, o);
+    const float rstd = rsqrtf(q * (1.f / C) + eps);
+    const float nmr = -mean * rstd;
+    if (ok) {
+#pragma unroll
+      for (int i = 0; i < 5; ++i) {
+        const int c = (lr + L * i) * 8;
+        const float4 g0 = *reinterpret_cast<const float4*>(sg + c), g1 = *reinterpret_cast<const float4*>(sg + c + 4);
+        const float4 b0 = *reinterpret_cast<const float4*>(sb + c), b1 = *reinterpret_cast<const float4*>(sb + c + 4);
+        Half8 ov;
+        ov.h[0] = __floats2half2_rn(fmaf(fmaf(v[i][0], rstd, nmr), g0.x, b0.x), fmaf(fmaf(v[i][1], rstd, nmr), g0.y, b0.y));
+        ov.h[1] = __floats2half2_rn(fmaf(fmaf(v[i][2], rstd, nmr), g0.z, b0.z), fmaf(fmaf(v[i][3], rstd, nmr), g0.w, b0.w));
+        ov.h[2] = __floats2half2_rn(fmaf(fmaf(v[i][4], rstd, nmr), g1.x, b1.x), fmaf(fmaf(v[i][5], rstd, nmr), g1.y, b1.y));
+        ov.h[3] = __floats2half2_rn(fmaf(fmaf(v[i][6], rstd, nmr), g1.z, b1.z), fmaf(fmaf(v[i][7], rstd, nmr), g1.w, b1.w));
+        *reinterpret_cast<Half8*>(y + row * C + c) = ov;
+      }
+    }
+  }
+}
+
 cudaError_t layernorm(cudaStream_t s, const __half* x, long long M, int C, float eps, const float* gamma,
                       const float* beta, __half* y) {
   ProfScope prof(s, KC_LAYERNORM);
   if (C % 8) return cudaErrorInvalidValue;
+  if (C == 320 || C == 640 || C == 1280) {
+    const int L = C / 40;
+    const long long groups = (M + 32 / L - 1) / (32 / L);
+    long long blocks = (groups + 7) / 8;
+    if (blocks > 148 * 8) blocks = 148 * 8;   // 8 resident blocks per SM, grid-stride over row groups
+    if (L == 8) layernorm40_kernel<8><<<(unsigned)blocks, 256, 0, s>>>(x, M, eps, gamma, beta, y);
+    else if (L == 16) layernorm40_kernel<16><<<(unsigned)blocks, 256, 0, s>>>(x, M, eps, gamma, beta, y);
+    else layernorm40_kernel<32><<<(unsigned)blocks, 256, 0, s>>>(x, M, eps, gamma, beta, y);
+    return cudaGetLastError();
+  }
   const int vecs = C / 8;
   auto blocks_for = [&](int R) { return (unsigned)((M + 8LL * R - 1) / (8LL * R)); };
   if (vecs <= 32) layernorm_kernel<1, 4><<<blocks_for(4), 256, 0, s>>>(x, M, C, eps, gamma, beta, y);

@@ -245,6 +245,15 @@ if __name__ == "__main__":
             e1.record(); torch.cuda.synchronize()
             ms = e0.elapsed_time(e1) / 10
             print(f"[bench] groupnorm+silu 34x4096x320 fps={fps}: {ms:.3f} ms  {3 * x.numel() * 2 / ms / 1e6:.0f} GB/s (2R+1W)", flush=True)
+        for (Ml, Cl) in ((139264, 320), (34816, 640)):
+            xl = torch.randn(Ml, Cl, device=dev).half()
+            gl = torch.ones(Cl, device=dev); bl = torch.zeros(Cl, device=dev)
+            for _ in range(2): ops.layernorm(xl, gl, bl, 1e-5)
+            e0.record()
+            for _ in range(10): ops.layernorm(xl, gl, bl, 1e-5)
+            e1.record(); torch.cuda.synchronize()
+            ms = e0.elapsed_time(e1) / 10
+            print(f"[bench] layernorm {Ml}x{Cl}: {ms:.3f} ms  {2 * xl.numel() * 2 / ms / 1e6:.0f} GB/s (1R+1W)", flush=True)
         qkv_t = torch.randn(2 * 17 * 4096, 3 * 8 * 48, device=dev).half()
         for _ in range(2): ops.temporal_attention(qkv_t, 2, 17, 4096, 8, 40, 48, 40 ** -0.5)
         e0.record()

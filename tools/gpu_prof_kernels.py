@@ -33,5 +33,15 @@ for _ in range(2):
 wq = (torch.randn(1152, 320, device=dev) / 320 ** 0.5).half()
 for _ in range(2):
     ops.conv_gemm(a, wq)
+# out-projection K=320 -> N=320 with residual
+wo = (torch.randn(320, 320, device=dev) / 320 ** 0.5).half()
+for _ in range(2):
+    ops.conv_gemm(a, wo, bias=b[:320].contiguous(), residual=res)
+# GroupNorm (4-D and 5-D statistics) and LayerNorm at level 0
+g = torch.randn(320, device=dev); be = torch.randn(320, device=dev)
+for _ in range(2):
+    ops.groupnorm(x.view(NF, 4096, 320), g, be, groups=32, frames_per_stat=1, silu=True)
+    ops.groupnorm(x.view(NF, 4096, 320), g, be, groups=32, frames_per_stat=17, silu=True)
+    ops.layernorm(res, g, be, 1e-5)
 torch.cuda.synchronize()
 print("done")
