@@ -51,30 +51,44 @@ __device__ __forceinline__ float gelu_fast(float x) {
   return 0.5f * x * (1.f + erf_v);
 }
 
-// value * gelu_erf(gate) for two columns at once. With w = 0.5 |x| poly(t) exp(-x^2/2) >= 0 (A&S 7.1.26),
-// gelu(x) = max(x, 0) - w for either sign of x.
+__device__ __forceinline__ float rcp_approx(float x) {
+  float y;
+  asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+  return y;
+}
+// value * gelu_erf(gate) for two columns at once. A&S 7.1.26: erfc(z) = t P(t) exp(-z^2), t = 1 / (1 + p z), z >= 0.
+// With u = |x| and w = 0.5 u erfc(u / sqrt 2) >= 0, gelu(x) = max(x, 0) - w for either sign of x. The reciprocal is
+// the SFU approximation (its argument lies in [1, inf), no special cases), -0.5 is folded into the coefficients.
 __device__ __forceinline__ F2 geglu2(F2 val, F2 gate) {
   float g0, g1;
   f2_get(gate, g0, g1);
-  const F2 ax = f2_make(fabsf(g0), fabsf(g1));
-  const F2 z = f2_mul(ax, f2_make(0.70710678118654752440f, 0.70710678118654752440f));
+  const F2 u = f2_make(fabsf(g0), fabsf(g1));
   float d0, d1;
-  f2_get(f2_fma(z, f2_make(0.3275911f, 0.3275911f), f2_make(1.f, 1.f)), d0, d1);
-  const F2 t = f2_make(__frcp_rn(d0), __frcp_rn(d1));
-  F2 poly = f2_fma(t, f2_make(1.061405429f, 1.061405429f), f2_make(-1.453152027f, -1.453152027f));
-  poly = f2_fma(poly, t, f2_make(1.421413741f, 1.421413741f));
-  poly = f2_fma(poly, t, f2_make(-0.284496736f, -0.284496736f));
-  poly = f2_fma(poly, t, f2_make(0.254829592f, 0.254829592f));
-  poly = f2_mul(poly, t);
+  f2_get(f2_fma(u, f2_make(0.231641888f, 0.231641888f), f2_make(1.f, 1.f)), d0, d1);   // 1 + p u / sqrt 2
+  const F2 t = f2_make(rcp_approx(d0), rcp_approx(d1));
+  F2 poly = f2_fma(t, f2_make(-0.5307027145f, -0.5307027145f), f2_make(0.7265760135f, 0.7265760135f));
+  poly = f2_fma(poly, t, f2_make(-0.7107068705f, -0.7107068705f));
+  poly = f2_fma(poly, t, f2_make(0.142248368f, 0.142248368f));
+  poly = f2_fma(poly, t, f2_make(-0.127414796f, -0.127414796f));
+  poly = f2_mul(poly, t);                                                                 // -0.5 t P(t)
   float a0, a1;
-  f2_get(f2_mul(f2_mul(z, z), f2_make(-1.4426950408889634f, -1.4426950408889634f)), a0, a1);
+  f2_get(f2_mul(f2_mul(u, f2_make(-0.72134752044f, -0.72134752044f)), u), a0, a1);        // -u^2 / 2 * log2 e
   float e0, e1;
   asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(e0) : "f"(a0));
   asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(e1) : "f"(a1));
-  const F2 w = f2_mul(f2_mul(ax, f2_make(-0.5f, -0.5f)), f2_mul(poly, f2_make(e0, e1)));   // -w
-  const F2 gelu = f2_add(f2_make(fmaxf(g0, 0.f), fmaxf(g1, 0.f)), w);
+  const F2 gelu = f2_fma(u, f2_mul(poly, f2_make(e0, e1)), f2_make(fmaxf(g0, 0.f), fmaxf(g1, 0.f)));
   return f2_mul(val, gelu);
 }
+
+// Epilogue variants (template parameter kEpi). The generic one takes every option at run time; the three fast ones
+// cover the shapes that are epilogue-bound in the UNet (K <= 640) with packed f32x2 arithmetic and no per-element
+// branches: ~2-3 instructions per output element instead of ~14.
+enum : int {
+  kEpiGeneric = 0,
+  kEpiPlain = 1,      // fp16 out, bias / row-add optional, alpha == 1, no residual, no activation, N % 32 == 0
+  kEpiResidual = 2,   // fp16 out, alpha * (acc + bias) + residual (beta == 1), N % 32 == 0
+  kEpiGeglu = 3       // fp16 out, value * gelu(gate) on the packed [16 value | 16 gate] column layout
+};
 
 // kTwoCta: the kernel runs as CTA pairs (cluster of 2, tcgen05 cta_group::2): one 256 x block_n tile per pair, each CTA
 // stages its own 128 A rows and HALF of the weight tile, the leader issues M=256 MMAs that read both halves. This cuts
@@ -84,7 +98,7 @@ struct AMaps {
   CUtensorMap m[4];   // activation views: [0] source 0, [1] skip-concat source / stride-2 phases 1..3
 };
 
-template <bool kTwoCta>
+template <bool kTwoCta, int kEpi>
 __global__ void __launch_bounds__(384, 1)
 conv_gemm_kernel(const __grid_constant__ AMaps tmA, const __grid_constant__ CUtensorMap tmB,
                  const __grid_constant__ CUtensorMap tmC,
@@ -270,109 +284,185 @@ conv_gemm_kernel(const __grid_constant__ AMaps tmA, const __grid_constant__ CUte
       tc_fence_after();
       const uint32_t t_row = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)as * kMaxBlockN;
       for (int c0 = half * acc_step; c0 < p.block_n; c0 += 2 * acc_step) {
-        // accumulator -> f[32] = the 32 output columns of this chunk, bias / row-add applied
-        float f[32];
-        const int nbase = ncol0 + c0;
-        if (p.geglu) {
-          uint32_t va[32], vb[32];
-          tmem_ld32(t_row + c0, va);
-          tmem_ld32(t_row + c0 + 32, vb);
+        if constexpr (kEpi != kEpiGeneric) {
+          const int nbase = ncol0 + c0;
+          uint32_t v[32], vg[32];
+          tmem_ld32(t_row + c0, v);
+          if constexpr (kEpi == kEpiGeglu) tmem_ld32(t_row + c0 + 32, vg);
+          if constexpr (kEpi == kEpiResidual) load_res(c0 + 2 * acc_step, rnxt);
           tmem_ld_wait();
-          // packed columns: [16 value | 16 gate] per 32 accumulator columns
+          if (nbase < p.N) {     // uniform per column half: the skipped chunks skip their barrier as a group
+            uint8_t* buf = staging + (half * kStagingDepth + (chunk_iter % kStagingDepth)) * kStagingBufBytes;
+            const F2 alpha2 = f2_make(p.alpha, p.alpha);
 #pragma unroll
-          for (int hsel = 0; hsel < 2; ++hsel) {
-            const uint32_t* v = hsel ? vb : va;
-            const int nb = nbase + hsel * 32;
+            for (int g = 0; g < 4; ++g) {      // 8 output columns = one 16-byte staging store
+              uint32_t o[4];
+              if constexpr (kEpi == kEpiGeglu) {
+                // output columns 8g..8g+7 of this chunk: accumulator block g/2 (va | vb), value j, gate 16 + j
+                const uint32_t* vv = (g < 2) ? v : vg;
+                const int nb = nbase + (g >> 1) * 32;
+                const int j0 = (g & 1) * 8;
 #pragma unroll
-            for (int j4 = 0; j4 < 4; ++j4) {
-              // bias of 4 value columns and their 4 gate columns (nb is a multiple of 32: 16-byte aligned float4)
-              const float4 bv = p.bias ? __ldg(reinterpret_cast<const float4*>(p.bias + nb) + j4) : make_float4(0, 0, 0, 0);
-              const float4 bg = p.bias ? __ldg(reinterpret_cast<const float4*>(p.bias + nb + 16) + j4) : make_float4(0, 0, 0, 0);
-              const int j = j4 * 4;
-              const F2 v01 = f2_add(f2_make(__uint_as_float(v[j]), __uint_as_float(v[j + 1])), f2_make(bv.x, bv.y));
-              const F2 v23 = f2_add(f2_make(__uint_as_float(v[j + 2]), __uint_as_float(v[j + 3])), f2_make(bv.z, bv.w));
-              const F2 g01 = f2_add(f2_make(__uint_as_float(v[16 + j]), __uint_as_float(v[16 + j + 1])), f2_make(bg.x, bg.y));
-              const F2 g23 = f2_add(f2_make(__uint_as_float(v[16 + j + 2]), __uint_as_float(v[16 + j + 3])), f2_make(bg.z, bg.w));
-              f2_get(geglu2(v01, g01), f[hsel * 16 + j], f[hsel * 16 + j + 1]);
-              f2_get(geglu2(v23, g23), f[hsel * 16 + j + 2], f[hsel * 16 + j + 3]);
+                for (int e = 0; e < 4; ++e) {
+                  const int j = j0 + 2 * e;
+                  float2 bv = make_float2(0.f, 0.f), bg = make_float2(0.f, 0.f);
+                  if (p.bias) {
+                    bv = __ldg(reinterpret_cast<const float2*>(p.bias + nb + j));
+                    bg = __ldg(reinterpret_cast<const float2*>(p.bias + nb + 16 + j));
+                  }
+                  const F2 val = f2_add(f2_make(__uint_as_float(vv[j]), __uint_as_float(vv[j + 1])), f2_make(bv.x, bv.y));
+                  const F2 gat = f2_add(f2_make(__uint_as_float(vv[16 + j]), __uint_as_float(vv[16 + j + 1])),
+                                        f2_make(bg.x, bg.y));
+                  float x0, x1;
+                  f2_get(geglu2(val, gat), x0, x1);
+                  const __half2 h2 = __floats2half2_rn(x0, x1);
+                  o[e] = *reinterpret_cast<const uint32_t*>(&h2);
+                }
+              } else {
+                float4 b0 = make_float4(0.f, 0.f, 0.f, 0.f), b1 = b0;
+                if (p.bias) {
+                  b0 = __ldg(reinterpret_cast<const float4*>(p.bias + nbase) + 2 * g);
+                  b1 = __ldg(reinterpret_cast<const float4*>(p.bias + nbase) + 2 * g + 1);
+                }
+                if (radd) {
+                  const float4 a0 = __ldg(reinterpret_cast<const float4*>(radd + nbase) + 2 * g);
+                  const float4 a1 = __ldg(reinterpret_cast<const float4*>(radd + nbase) + 2 * g + 1);
+                  b0.x += a0.x; b0.y += a0.y; b0.z += a0.z; b0.w += a0.w;
+                  b1.x += a1.x; b1.y += a1.y; b1.z += a1.z; b1.w += a1.w;
+                }
+                const float bb[8] = {b0.x, b0.y, b0.z, b0.w, b1.x, b1.y, b1.z, b1.w};
+                const __half2* rh2 = reinterpret_cast<const __half2*>(&rcur[g]);
+#pragma unroll
+                for (int e = 0; e < 4; ++e) {
+                  const int j = g * 8 + 2 * e;
+                  F2 x = f2_add(f2_make(__uint_as_float(v[j]), __uint_as_float(v[j + 1])), f2_make(bb[2 * e], bb[2 * e + 1]));
+                  if constexpr (kEpi == kEpiResidual) {
+                    const float2 rr = __half22float2(rh2[e]);
+                    x = f2_fma(x, alpha2, f2_make(rr.x, rr.y));
+                  }
+                  float x0, x1;
+                  f2_get(x, x0, x1);
+                  const __half2 h2 = __floats2half2_rn(x0, x1);
+                  o[e] = *reinterpret_cast<const uint32_t*>(&h2);
+                }
+              }
+              *reinterpret_cast<uint4*>(buf + r * 64 + ((g ^ ((r >> 1) & 3)) << 4)) = make_uint4(o[0], o[1], o[2], o[3]);
             }
+            fence_proxy_async();
+            if (issuer) tma_store_wait_read<kStagingDepth - 2>();
+            named_bar_sync(1 + half, 128);
+            if (issuer) {
+              const int oc = (kEpi == kEpiGeglu) ? nbase / 2 : nbase;
+              tma_store_4d(&tmC, buf, oc, tw * p.bw, th * p.bh, tn * p.bn);
+              tma_store_commit();
+            }
+            ++chunk_iter;
           }
         } else {
-          uint32_t v[32];
-          tmem_ld32(t_row + c0, v);      // block_n is a multiple of 32
-          load_res(c0 + 2 * acc_step, rnxt);
-          tmem_ld_wait();
-          if (nbase + 32 <= p.N) {
-#pragma unroll
-            for (int g = 0; g < 8; ++g) {
-              float4 b = p.bias ? __ldg(reinterpret_cast<const float4*>(p.bias + nbase) + g) : make_float4(0, 0, 0, 0);
-              if (radd) {
-                const float4 a4 = __ldg(reinterpret_cast<const float4*>(radd + nbase) + g);
-                b.x += a4.x; b.y += a4.y; b.z += a4.z; b.w += a4.w;
+          // accumulator -> f[32] = the 32 output columns of this chunk, bias / row-add applied
+          float f[32];
+          const int nbase = ncol0 + c0;
+          if (p.geglu) {
+            uint32_t va[32], vb[32];
+            tmem_ld32(t_row + c0, va);
+            tmem_ld32(t_row + c0 + 32, vb);
+            tmem_ld_wait();
+            // packed columns: [16 value | 16 gate] per 32 accumulator columns
+  #pragma unroll
+            for (int hsel = 0; hsel < 2; ++hsel) {
+              const uint32_t* v = hsel ? vb : va;
+              const int nb = nbase + hsel * 32;
+  #pragma unroll
+              for (int j4 = 0; j4 < 4; ++j4) {
+                // bias of 4 value columns and their 4 gate columns (nb is a multiple of 32: 16-byte aligned float4)
+                const float4 bv = p.bias ? __ldg(reinterpret_cast<const float4*>(p.bias + nb) + j4) : make_float4(0, 0, 0, 0);
+                const float4 bg = p.bias ? __ldg(reinterpret_cast<const float4*>(p.bias + nb + 16) + j4) : make_float4(0, 0, 0, 0);
+                const int j = j4 * 4;
+                const F2 v01 = f2_add(f2_make(__uint_as_float(v[j]), __uint_as_float(v[j + 1])), f2_make(bv.x, bv.y));
+                const F2 v23 = f2_add(f2_make(__uint_as_float(v[j + 2]), __uint_as_float(v[j + 3])), f2_make(bv.z, bv.w));
+                const F2 g01 = f2_add(f2_make(__uint_as_float(v[16 + j]), __uint_as_float(v[16 + j + 1])), f2_make(bg.x, bg.y));
+                const F2 g23 = f2_add(f2_make(__uint_as_float(v[16 + j + 2]), __uint_as_float(v[16 + j + 3])), f2_make(bg.z, bg.w));
+                f2_get(geglu2(v01, g01), f[hsel * 16 + j], f[hsel * 16 + j + 1]);
+                f2_get(geglu2(v23, g23), f[hsel * 16 + j + 2], f[hsel * 16 + j + 3]);
               }
-              f[g * 4 + 0] = __uint_as_float(v[g * 4 + 0]) + b.x;
-              f[g * 4 + 1] = __uint_as_float(v[g * 4 + 1]) + b.y;
-              f[g * 4 + 2] = __uint_as_float(v[g * 4 + 2]) + b.z;
-              f[g * 4 + 3] = __uint_as_float(v[g * 4 + 3]) + b.w;
             }
           } else {
-#pragma unroll
-            for (int j = 0; j < 32; ++j) {
-              const int nn = nbase + j;
-              float x = __uint_as_float(v[j]);
-              if (nn < p.N) {
-                if (p.bias) x += __ldg(p.bias + nn);
-                if (radd) x += __ldg(radd + nn);
+            uint32_t v[32];
+            tmem_ld32(t_row + c0, v);      // block_n is a multiple of 32
+            load_res(c0 + 2 * acc_step, rnxt);
+            tmem_ld_wait();
+            if (nbase + 32 <= p.N) {
+  #pragma unroll
+              for (int g = 0; g < 8; ++g) {
+                float4 b = p.bias ? __ldg(reinterpret_cast<const float4*>(p.bias + nbase) + g) : make_float4(0, 0, 0, 0);
+                if (radd) {
+                  const float4 a4 = __ldg(reinterpret_cast<const float4*>(radd + nbase) + g);
+                  b.x += a4.x; b.y += a4.y; b.z += a4.z; b.w += a4.w;
+                }
+                f[g * 4 + 0] = __uint_as_float(v[g * 4 + 0]) + b.x;
+                f[g * 4 + 1] = __uint_as_float(v[g * 4 + 1]) + b.y;
+                f[g * 4 + 2] = __uint_as_float(v[g * 4 + 2]) + b.z;
+                f[g * 4 + 3] = __uint_as_float(v[g * 4 + 3]) + b.w;
               }
-              f[j] = x;
+            } else {
+  #pragma unroll
+              for (int j = 0; j < 32; ++j) {
+                const int nn = nbase + j;
+                float x = __uint_as_float(v[j]);
+                if (nn < p.N) {
+                  if (p.bias) x += __ldg(p.bias + nn);
+                  if (radd) x += __ldg(radd + nn);
+                }
+                f[j] = x;
+              }
             }
           }
-        }
-        if (p.out_f32) {
-          if (row_ok) {
-#pragma unroll
-            for (int g = 0; g < 8; ++g) {
-              const int nn = nbase + g * 4;
-              if (nn < p.N) {
-                float4 o4;
-                o4.x = f[g * 4 + 0] * p.alpha; o4.y = f[g * 4 + 1] * p.alpha;
-                o4.z = f[g * 4 + 2] * p.alpha; o4.w = f[g * 4 + 3] * p.alpha;
-                if (p.act == 1) { o4.x = silu(o4.x); o4.y = silu(o4.y); o4.z = silu(o4.z); o4.w = silu(o4.w); }
-                *reinterpret_cast<float4*>(reinterpret_cast<float*>(p.out) + m * p.ldc + nn) = o4;
+          if (p.out_f32) {
+            if (row_ok) {
+  #pragma unroll
+              for (int g = 0; g < 8; ++g) {
+                const int nn = nbase + g * 4;
+                if (nn < p.N) {
+                  float4 o4;
+                  o4.x = f[g * 4 + 0] * p.alpha; o4.y = f[g * 4 + 1] * p.alpha;
+                  o4.z = f[g * 4 + 2] * p.alpha; o4.w = f[g * 4 + 3] * p.alpha;
+                  if (p.act == 1) { o4.x = silu(o4.x); o4.y = silu(o4.y); o4.z = silu(o4.z); o4.w = silu(o4.w); }
+                  *reinterpret_cast<float4*>(reinterpret_cast<float*>(p.out) + m * p.ldc + nn) = o4;
+                }
               }
             }
-          }
-        } else {
-          // finish in fp32, round to fp16, stage, store
-          // staging ring of kStagingDepth buffers, ONE barrier per chunk: chunk i is written while stores i-1..i-3 drain
-          // (a TMA store takes ~1 us to release its smem source); before barrier i the issuer makes sure store
-          // i-(depth-1) is done, so after the barrier everybody knows the buffer of chunk i+1 is free
-          uint8_t* buf = staging + (half * kStagingDepth + (chunk_iter % kStagingDepth)) * kStagingBufBytes;
-#pragma unroll
-          for (int g = 0; g < 4; ++g) {
-            __align__(16) __half o[8];
-            const __half* rh8 = reinterpret_cast<const __half*>(&rcur[g]);
-#pragma unroll
-            for (int j = 0; j < 8; ++j) {
-              float x = f[g * 8 + j];
-              if (!p.geglu) {
-                x *= p.alpha;
-                if (use_res) x = fmaf(p.beta, __half2float(rh8[j]), x);
-                if (p.act == 1) x = silu(x);
+          } else {
+            // finish in fp32, round to fp16, stage, store
+            // staging ring of kStagingDepth buffers, ONE barrier per chunk: chunk i is written while stores i-1..i-3 drain
+            // (a TMA store takes ~1 us to release its smem source); before barrier i the issuer makes sure store
+            // i-(depth-1) is done, so after the barrier everybody knows the buffer of chunk i+1 is free
+            uint8_t* buf = staging + (half * kStagingDepth + (chunk_iter % kStagingDepth)) * kStagingBufBytes;
+  #pragma unroll
+            for (int g = 0; g < 4; ++g) {
+              __align__(16) __half o[8];
+              const __half* rh8 = reinterpret_cast<const __half*>(&rcur[g]);
+  #pragma unroll
+              for (int j = 0; j < 8; ++j) {
+                float x = f[g * 8 + j];
+                if (!p.geglu) {
+                  x *= p.alpha;
+                  if (use_res) x = fmaf(p.beta, __half2float(rh8[j]), x);
+                  if (p.act == 1) x = silu(x);
+                }
+                o[j] = __float2half_rn(x);
               }
-              o[j] = __float2half_rn(x);
+              *reinterpret_cast<uint4*>(buf + r * 64 + ((g ^ ((r >> 1) & 3)) << 4)) = *reinterpret_cast<const uint4*>(o);
             }
-            *reinterpret_cast<uint4*>(buf + r * 64 + ((g ^ ((r >> 1) & 3)) << 4)) = *reinterpret_cast<const uint4*>(o);
+            fence_proxy_async();
+            if (issuer) tma_store_wait_read<kStagingDepth - 2>();
+            named_bar_sync(1 + half, 128);
+            if (issuer) {
+              const int oc = p.geglu ? nbase / 2 : nbase;
+              tma_store_4d(&tmC, buf, oc, tw * p.bw, th * p.bh, tn * p.bn);
+              tma_store_commit();
+            }
+            ++chunk_iter;
           }
-          fence_proxy_async();
-          if (issuer) tma_store_wait_read<kStagingDepth - 2>();
-          named_bar_sync(1 + half, 128);
-          if (issuer) {
-            const int oc = p.geglu ? nbase / 2 : nbase;
-            tma_store_4d(&tmC, buf, oc, tw * p.bw, th * p.bh, tn * p.bn);
-            tma_store_commit();
-          }
-          ++chunk_iter;
         }
 #pragma unroll
         for (int g = 0; g < 4; ++g) rcur[g] = rnxt[g];
@@ -479,12 +569,21 @@ static int pick_block_n(int N, int geglu, long long tiles_m, int num_sms) {
 
 static cudaError_t launch_common(cudaStream_t stream, const CUtensorMap* maps, int nmaps, ConvGemmParams& p,
                                  const __half* wt, long long ktot, const Epilogue& ep, int num_sms, const char** err) {
+  // kernel variants indexed [cta pair][epilogue]
+  typedef void (*KernelFn)(const AMaps, const CUtensorMap, const CUtensorMap, const ConvGemmParams);
+  static const KernelFn kernels[2][4] = {
+      {conv_gemm_kernel<false, kEpiGeneric>, conv_gemm_kernel<false, kEpiPlain>, conv_gemm_kernel<false, kEpiResidual>,
+       conv_gemm_kernel<false, kEpiGeglu>},
+      {conv_gemm_kernel<true, kEpiGeneric>, conv_gemm_kernel<true, kEpiPlain>, conv_gemm_kernel<true, kEpiResidual>,
+       conv_gemm_kernel<true, kEpiGeglu>}};
   static bool attr_set = false;
   if (!attr_set) {
-    cudaError_t e = cudaFuncSetAttribute(conv_gemm_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemBytes);
-    if (e == cudaSuccess)
-      e = cudaFuncSetAttribute(conv_gemm_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemBytes);
-    if (e != cudaSuccess) { *err = "cudaFuncSetAttribute(conv_gemm_kernel)"; return e; }
+    for (int a = 0; a < 2; ++a)
+      for (int b = 0; b < 4; ++b) {
+        cudaError_t e = cudaFuncSetAttribute(reinterpret_cast<const void*>(kernels[a][b]),
+                                             cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemBytes);
+        if (e != cudaSuccess) { *err = "cudaFuncSetAttribute(conv_gemm_kernel)"; return e; }
+      }
     attr_set = true;
   }
   const long long tiles_m = (long long)p.tiles_w * p.tiles_h * p.tiles_n;
@@ -530,16 +629,26 @@ static cudaError_t launch_common(cudaStream_t stream, const CUtensorMap* maps, i
   const long long num_tiles = tiles_m * p.tiles_nn;
   int grid = (int)(num_tiles < num_sms ? num_tiles : num_sms);
   if (two_cta) grid = (int)(2 * (pair_units < num_sms / 2 ? pair_units : num_sms / 2));
+  // epilogue variant: the fast ones need whole 32-column chunks and the common alpha / beta
+  static const int epi_env = getenv("MVB_EPI") ? atoi(getenv("MVB_EPI")) : -1;   // 0 forces the generic epilogue
+  int epi = kEpiGeneric;
+  if (!ep.out_f32 && ep.act == 0 && epi_env != 0) {
+    if (ep.geglu) { if (p.N % 64 == 0 && !ep.rowadd) epi = kEpiGeglu; }
+    else if (p.N % 32 == 0) {
+      if (ep.res && ep.beta == 1.f) epi = kEpiResidual;
+      else if (!ep.res && ep.alpha == 1.f) epi = kEpiPlain;
+    }
+  }
   static const bool trace = getenv("MVB_TRACE") != nullptr;
   if (trace)
-    fprintf(stderr, "MVB_TRACE gemm M=%lld N=%d K=%lld taps=%d block_n=%d tiles=%lld geglu=%d res=%d f32=%d cta2=%d\n",
+    fprintf(stderr, "MVB_TRACE gemm M=%lld N=%d K=%lld taps=%d block_n=%d tiles=%lld geglu=%d res=%d f32=%d cta2=%d epi=%d\n",
             (long long)p.W * p.H * p.NF, p.N, ktot, p.ntaps, p.block_n, num_tiles, p.geglu, p.res != nullptr, p.out_f32,
-            (int)two_cta);
+            (int)two_cta, epi);
   AMaps am;
   for (int i = 0; i < 4; ++i) am.m[i] = maps[i < nmaps ? i : 0];
   ProfScope prof(stream, KC_GEMM);
   cudaError_t e;
-  if (two_cta) {
+  {
     cudaLaunchConfig_t cfg{};
     cfg.gridDim = dim3(grid);
     cfg.blockDim = dim3(384);
@@ -549,11 +658,8 @@ static cudaError_t launch_common(cudaStream_t stream, const CUtensorMap* maps, i
     at[0].id = cudaLaunchAttributeClusterDimension;
     at[0].val.clusterDim.x = 2; at[0].val.clusterDim.y = 1; at[0].val.clusterDim.z = 1;
     cfg.attrs = at;
-    cfg.numAttrs = 1;
-    e = cudaLaunchKernelEx(&cfg, conv_gemm_kernel<true>, am, tmB, tmC, p);
-  } else {
-    conv_gemm_kernel<false><<<grid, 384, kSmemBytes, stream>>>(am, tmB, tmC, p);
-    e = cudaGetLastError();
+    cfg.numAttrs = two_cta ? 1 : 0;
+    e = cudaLaunchKernelEx(&cfg, kernels[two_cta ? 1 : 0][epi], am, tmB, tmC, p);
   }
   if (e != cudaSuccess) *err = "conv_gemm_kernel launch";
   return e;

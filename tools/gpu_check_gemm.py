@@ -113,6 +113,25 @@ def bench(NF, H, W, C, N, taps, iters=10):
     print(f"[bench] NF={NF} {H}x{W} C={C} N={N} taps={len(taps)}: {ms:.3f} ms  {fl / ms / 1e9:.1f} TFLOP/s", flush=True)
 
 
+def bench2(M, K, N, geglu=False, res=False, iters=10):
+    a = torch.randn(1, 1, M, K, device=dev).half()
+    w = (torch.randn(N, K, device=dev) / K ** 0.5).half()
+    b = torch.randn(N, device=dev)
+    r = torch.randn(M, N, device=dev).half() if res else None
+    out = torch.empty(M, N // 2 if geglu else N, device=dev, dtype=torch.half)
+    for _ in range(3):
+        ops.conv_gemm(a, w, bias=b, geglu=geglu, residual=r, out=out)
+    torch.cuda.synchronize()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(iters):
+        ops.conv_gemm(a, w, bias=b, geglu=geglu, residual=r, out=out)
+    e1.record()
+    torch.cuda.synchronize()
+    ms = e0.elapsed_time(e1) / iters
+    print(f"[bench] M={M} K={K} N={N} geglu={geglu} res={res}: {ms:.3f} ms  {2.0 * M * N * K / ms / 1e9:.1f} TFLOP/s", flush=True)
+
+
 if __name__ == "__main__":
     print(torch.cuda.get_device_name(0), flush=True)
     ok = True
@@ -122,6 +141,12 @@ if __name__ == "__main__":
     ok &= case_plain(1000, 320, 320, bias=True)
     ok &= case_plain(4096, 1280, 1280, bias=True, res=True, alpha=0.5, beta=2.0)
     ok &= case_plain(100, 64, 48)
+    ok &= case_plain(4096, 1280, 1280, bias=True, res=True, alpha=0.5)        # fast residual epilogue, CTA pairs
+    ok &= case_plain(1000, 320, 320, bias=True, res=True, alpha=0.37)         # fast residual epilogue, ragged M
+    ok &= case_plain(40000, 320, 1152)                                         # fast plain epilogue, no bias
+    ok &= case_plain(777, 640, 96, bias=True)                                  # N % 32 == 0, N < block tile
+    ok &= case_geglu(139264 // 8, 320, 1280)
+    ok &= case_geglu(1000, 640, 2560)
     ok &= case_conv3x3(2, 16, 16, 64, 64)
     ok &= case_conv3x3(3, 8, 8, 128, 320)
     ok &= case_conv3x3(2, 64, 64, 320, 320)
@@ -140,3 +165,8 @@ if __name__ == "__main__":
         bench(1, 1, 139264, 320, 2560, ops.TAPS_1)
         bench(1, 1, 139264, 1280, 320, ops.TAPS_1)
         bench(1, 1, 8192, 8192, 8192, ops.TAPS_1)
+        bench2(139264, 320, 2560, geglu=True)
+        bench2(34816, 640, 5120, geglu=True)
+        bench2(139264, 320, 320, res=True)
+        bench2(34816, 640, 640, res=True)
+        bench2(139264, 320, 1152)
