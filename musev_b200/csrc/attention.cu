@@ -38,7 +38,6 @@ struct AttnParams {
 };
 
 static constexpr int kAtomBytes = 128 * 128;  // 128 rows x 64 fp16
-static constexpr int kPolyOf8 = 3;             // of every 8 column pairs, this many take the FMA-pipe exp2
 
 // 2^x for a pair of arguments on the FMA / ALU pipes (no SFU): round-to-nearest split x = n + f, |f| <= 0.5, degree-3
 // minimax polynomial for 2^f (relative error < 7.5e-5, well below the 4.9e-4 fp16 rounding of P), exponent patched in
@@ -74,7 +73,8 @@ __device__ __forceinline__ void tile_info(const AttnParams& p, int j, int* seg, 
   }
 }
 
-template <bool kSumInV>
+// kPolyOf8: of every 8 column pairs, this many take the FMA-pipe exp2 (the rest go to the SFU)
+template <bool kSumInV, int kPolyOf8>
 __global__ void __launch_bounds__(320, 2)
 attention_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUtensorMap tmK0,
                  const __grid_constant__ CUtensorMap tmV0, const __grid_constant__ CUtensorMap tmK1,
@@ -390,11 +390,21 @@ cudaError_t launch_attention(cudaStream_t stream, const AttnArgs& a, const char*
   else { p.sk = 1; p.sv = 1; }
   p.tmem_cols = (128 + a.dp <= 256) ? 256 : 512;
   const int smem = (1 + p.sk + p.sv) * p.natoms * kAtomBytes + 2 * kAtomBytes + 1024 + 128 + 2048;
+  typedef void (*KernelFn)(const CUtensorMap, const CUtensorMap, const CUtensorMap, const CUtensorMap, const CUtensorMap,
+                           const AttnParams);
+  static const KernelFn kernels[2][4] = {
+      {attention_kernel<false, 0>, attention_kernel<false, 2>, attention_kernel<false, 3>, attention_kernel<false, 4>},
+      {attention_kernel<true, 0>, attention_kernel<true, 2>, attention_kernel<true, 3>, attention_kernel<true, 4>}};
+  // share of the exp2 work moved from the SFU to the FMA pipe: 0, 2/8 (default), 3/8 or 4/8 (env MVB_POLY, experiments)
+  static const int poly_env = getenv("MVB_POLY") ? atoi(getenv("MVB_POLY")) : 2;
+  const int poly_idx = poly_env <= 0 ? 0 : poly_env == 2 ? 1 : poly_env >= 4 ? 3 : 2;
   static int max_set = 0;
   if (smem > max_set) {
-    cudaError_t e = cudaFuncSetAttribute(attention_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
-    if (e == cudaSuccess)
-      e = cudaFuncSetAttribute(attention_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
+    cudaError_t e = cudaSuccess;
+    for (int a = 0; a < 2 && e == cudaSuccess; ++a)
+      for (int b = 0; b < 4 && e == cudaSuccess; ++b)
+        e = cudaFuncSetAttribute(reinterpret_cast<const void*>(kernels[a][b]), cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                 227 * 1024);
     if (e != cudaSuccess) { *err = "cudaFuncSetAttribute(attention_kernel)"; return e; }
     max_set = 227 * 1024;
   }
@@ -417,8 +427,7 @@ cudaError_t launch_attention(cudaStream_t stream, const AttnArgs& a, const char*
             p.nk[1], a.accumulate);
   dim3 grid((a.Nq + 127) / 128, a.heads, a.NF);
   ProfScope prof(stream, KC_ATTENTION);
-  if (p.sum_in_v) attention_kernel<true><<<grid, 320, smem, stream>>>(tq, tk0, tv0, tk1, tv1, p);
-  else attention_kernel<false><<<grid, 320, smem, stream>>>(tq, tk0, tv0, tk1, tv1, p);
+  kernels[p.sum_in_v ? 1 : 0][poly_idx]<<<grid, 320, smem, stream>>>(tq, tk0, tv0, tk1, tv1, p);
   cudaError_t e = cudaGetLastError();
   if (e != cudaSuccess) *err = "attention_kernel launch";
   return e;

@@ -27,7 +27,8 @@ gn_stats_kernel(const __half* __restrict__ x0, int C0, const __half* __restrict_
   const int vecs = C / 8;
   const int pairs = C / 2;
   const int cpg2 = (C / G) / 2;      // channel pairs per group
-  const int f = blockIdx.y;
+  // frames in reverse order: the tail of the tensor is what the producing GEMM wrote last and is still in L2
+  const int f = gridDim.y - 1 - blockIdx.y;
   const int chunks = gridDim.x;
   const int cols_per_pass = vecs < (int)blockDim.x ? vecs : (int)blockDim.x;
   const int rows_per_iter = blockDim.x / cols_per_pass;
@@ -105,26 +106,23 @@ cudaError_t gn_stats(cudaStream_t s, const __half* x0, int C0, const __half* x1,
 }
 
 // Reduces the per-frame partials of one statistics group (fps consecutive frames) to mean / rstd per group:
-// stats[NF/fps][G][2]. grid NF/fps, block 32*? threads (one thread per group).
+// stats[NF/fps][G][2]. grid (NF/fps, G), one warp per (statistics group, channel group): lanes walk the partials in a
+// fixed interleaved order, then a fixed shuffle tree -- deterministic.
 __global__ void gn_finalize_kernel(const float* __restrict__ part, int chunks, int fps, int G, float count, float eps,
                                    float* __restrict__ stats) {
-  // 8 lanes per group walk the partials in a fixed interleaved order, then a fixed shuffle tree: deterministic
-  const int sg = blockIdx.x;
-  const int g = threadIdx.x >> 3, sub = threadIdx.x & 7;
+  const int sg = blockIdx.x, g = blockIdx.y, lane = threadIdx.x;
   float s = 0.f, q = 0.f;
-  if (g < G) {
-    for (int i = sub; i < fps * chunks; i += 8) {
-      const float* pp = part + ((size_t)sg * fps * chunks + i) * 2 * G + 2 * g;
-      s += pp[0];
-      q += pp[1];
-    }
+  for (int i = lane; i < fps * chunks; i += 32) {
+    const float2 pp = *reinterpret_cast<const float2*>(part + ((size_t)sg * fps * chunks + i) * 2 * G + 2 * g);
+    s += pp.x;
+    q += pp.y;
   }
 #pragma unroll
-  for (int o = 4; o > 0; o >>= 1) {
+  for (int o = 16; o > 0; o >>= 1) {
     s += __shfl_xor_sync(0xffffffffu, s, o);
     q += __shfl_xor_sync(0xffffffffu, q, o);
   }
-  if (g < G && sub == 0) {
+  if (lane == 0) {
     const float mean = s / count;
     float var = q / count - mean * mean;
     var = var < 0.f ? 0.f : var;
@@ -223,7 +221,7 @@ cudaError_t gn_apply(cudaStream_t s, const __half* x0, int C0, const __half* x1,
   // mean / rstd live right behind the partial sums in the caller's scratch: NF*(kGnMaxChunks+1)*G*2 floats in total
   float* stats = const_cast<float*>(part) + (size_t)NF * kGnMaxChunks * G * 2;
   const float count = (float)fps * HW * (C / G);
-  gn_finalize_kernel<<<NF / fps, ((G * 8 + 31) / 32) * 32, 0, s>>>(part, chunks, fps, G, count, eps, stats);
+  gn_finalize_kernel<<<dim3(NF / fps, G), 32, 0, s>>>(part, chunks, fps, G, count, eps, stats);
   // ~64 KB of fp16 per block, block size a multiple of the number of channel vectors when possible
   const int vecs = C / 8;
   int threads = 256;
