@@ -83,6 +83,7 @@ typedef struct mvb_attention_desc {
   float out_scale;
   int accumulate;
   int v_ones_col;  /* every V row holds 1.0 at column h*dp + d (dp > d): the P.V MMA also yields the softmax row sum */
+  int variant;     /* 0: default kernel; 2: split-KV kernel (dp <= 64 only; two independent softmax groups, kept for A/B runs) */
 } mvb_attention_desc;
 
 int mvb_op_attention(const mvb_attention_desc* desc, void* stream);

@@ -39,7 +39,7 @@ class AttentionDesc(C.Structure):
         ("k", C.c_void_p * 2), ("v", C.c_void_p * 2), ("ldkv", C.c_longlong * 2), ("kv_rows", C.c_longlong * 2),
         ("nk", C.c_int * 2), ("fdiv", C.c_int * 2), ("fmul", C.c_longlong * 2), ("fadd", C.c_longlong * 2),
         ("out", C.c_void_p), ("ldo", C.c_longlong),
-        ("out_scale", C.c_float), ("accumulate", C.c_int), ("v_ones_col", C.c_int),
+        ("out_scale", C.c_float), ("accumulate", C.c_int), ("v_ones_col", C.c_int), ("variant", C.c_int),
     ]
 
 

@@ -365,6 +365,303 @@ attention_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant_
   if (warp == 1) tmem_dealloc(tmem_base, (uint32_t)p.tmem_cols);
 }
 
+// ------------------------------------------------------------------------------------------------ split-KV variant
+// Same math, different decomposition, for head dims that fit one 64-column atom (dp <= 64: level 0, where attention
+// time is). The 128-query tile is served by TWO independent softmax groups of 4 warps; group g owns the 64-key tiles
+// j = g, g+2, g+4, ... with its own S tile, P buffer, running max and O accumulator in TMEM, and the two partial
+// results are merged once at the end (O = (O_A 2^(mA-M) + O_B 2^(mB-M)) / (lA' + lB')), as in split-KV decoding. One
+// thread owns a whole row of its tile, so the main loop has no cross-thread exchange and no intra-CTA barrier; with
+// two CTAs per SM there are four independent softmax pipelines per SM whose phases (TMEM load / max / exp / P store)
+// interleave instead of running in lock step.
+//   TMEM (256 columns): S_A 0..63 | S_B 64..127 | O_A 128..191 | O_B 192..255.
+//   smem: Q 16 KB | K ring 3 x 8 KB | V ring 3 x 8 KB | P_A, P_B 16 KB each | barriers | (m, l) exchange.
+static constexpr int kSplitStages = 3;
+static constexpr int kKvTileBytes = 64 * 128;   // 64 keys x 64 fp16
+
+template <bool kSumInV>
+__global__ void __launch_bounds__(320, 2)
+attention_split_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUtensorMap tmK0,
+                       const __grid_constant__ CUtensorMap tmV0, const __grid_constant__ CUtensorMap tmK1,
+                       const __grid_constant__ CUtensorMap tmV1, const __grid_constant__ AttnParams p) {
+  constexpr int kPolyOf8 = 2;
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  uint8_t* sQ = smem;
+  uint8_t* sK = sQ + kAtomBytes;
+  uint8_t* sV = sK + kSplitStages * kKvTileBytes;
+  uint8_t* sP = sV + kSplitStages * kKvTileBytes;          // [2 groups][128 rows][64 keys]
+  uint64_t* bars = reinterpret_cast<uint64_t*>(sP + 2 * kAtomBytes);
+  uint64_t* bar_q = bars;
+  uint64_t* full_k = bars + 1;                   // [3]
+  uint64_t* empty_k = bars + 4;                  // [3]
+  uint64_t* full_v = bars + 7;                   // [3]
+  uint64_t* empty_v = bars + 10;                 // [3]
+  uint64_t* bar_s = bars + 13;                   // [2] S_g ready
+  uint64_t* bar_sfree = bars + 15;               // [2] group g holds S in registers (128 arrivals)
+  uint64_t* bar_p = bars + 17;                   // [2] P_g written, O_g rescaled (128 arrivals)
+  uint64_t* bar_pv = bars + 19;                  // [2] P_g V done: P_g reusable, O_g stable
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 21);
+  float* xch = reinterpret_cast<float*>(bars + 22);        // [2 groups][128 rows] (m, l)
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int q0 = blockIdx.x * 128;
+  const int h = blockIdx.y;
+  const int f = blockIdx.z;
+  const int t0 = (p.nk[0] + 63) / 64;
+  const int ntiles = t0 + (p.nseg > 1 ? (p.nk[1] + 63) / 64 : 0);
+
+  if (warp == 0 && lane == 0) {
+    tma_prefetch_desc(&tmQ); tma_prefetch_desc(&tmK0); tma_prefetch_desc(&tmV0);
+    mbar_init(bar_q, 1);
+    for (int s = 0; s < kSplitStages; ++s) {
+      mbar_init(&full_k[s], 1); mbar_init(&empty_k[s], 1);
+      mbar_init(&full_v[s], 1); mbar_init(&empty_v[s], 1);
+    }
+    for (int g = 0; g < 2; ++g) {
+      mbar_init(&bar_s[g], 1); mbar_init(&bar_sfree[g], 128);
+      mbar_init(&bar_p[g], 128); mbar_init(&bar_pv[g], 1);
+    }
+    fence_barrier_init();
+  }
+  if (warp == 1) {
+    tmem_alloc(tmem_slot, 256u);
+    tmem_relinquish();
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  // key rows of tile j in its segment's K / V matrix
+  auto tile_row = [&](int j, int* seg) -> long long {
+    const int sg = j < t0 ? 0 : 1;
+    *seg = sg;
+    const int k0 = (sg ? j - t0 : j) * 64;
+    return (long long)(f / p.fdiv[sg]) * p.fmul[sg] + p.fadd[sg] + k0;
+  };
+
+  if (warp == 0) {
+    if (elect_one()) {
+      mbar_expect_tx(bar_q, (uint32_t)kAtomBytes);
+      tma_load_2d(sQ, &tmQ, bar_q, h * p.dp, f * p.Nq + q0);
+    }
+    __syncwarp();
+    auto load_k = [&](int j) {
+      int seg;
+      const long long row = tile_row(j, &seg);
+      const int st = j % kSplitStages;
+      mbar_wait(&empty_k[st], ((j / kSplitStages) & 1) ^ 1);
+      if (elect_one()) {
+        mbar_expect_tx(&full_k[st], (uint32_t)kKvTileBytes);
+        tma_load_2d(sK + st * kKvTileBytes, seg ? &tmK1 : &tmK0, &full_k[st], h * p.dp, (int)row);
+      }
+      __syncwarp();
+    };
+    load_k(0);
+    if (ntiles > 1) load_k(1);
+    for (int j = 0; j < ntiles; ++j) {
+      if (j + 2 < ntiles) load_k(j + 2);     // K runs two tiles ahead: S_{j+2} is computed under softmax j
+      int seg;
+      const long long row = tile_row(j, &seg);
+      const int st = j % kSplitStages;
+      mbar_wait(&empty_v[st], ((j / kSplitStages) & 1) ^ 1);
+      if (elect_one()) {
+        mbar_expect_tx(&full_v[st], (uint32_t)kKvTileBytes);
+        tma_load_2d(sV + st * kKvTileBytes, seg ? &tmV1 : &tmV0, &full_v[st], h * p.dp, (int)row);
+      }
+      __syncwarp();
+    }
+  } else if (warp == 1) {
+    const uint32_t idesc_s = make_idesc_f16(128, 64, 0, 0);
+    const uint32_t idesc_o = make_idesc_f16(128, p.dp, 0, 1);   // B (= V) is MN-major
+    const int ksteps = p.dp / 16;
+    mbar_wait(bar_q, 0);
+    const uint32_t aQ = smem_u32(sQ);
+    auto issue_s = [&](int j) {
+      const int st = j % kSplitStages;
+      mbar_wait(&full_k[st], (j / kSplitStages) & 1);
+      tc_fence_after();
+      const uint32_t aK = smem_u32(sK + st * kKvTileBytes);
+      if (elect_one()) {
+        for (int kk = 0; kk < ksteps; ++kk)
+          umma_f16_ss(tmem_base + (uint32_t)(j & 1) * 64, make_desc_k_sw128(aQ + kk * 32), make_desc_k_sw128(aK + kk * 32),
+                      idesc_s, kk != 0);
+        umma_commit(&empty_k[st]);
+        umma_commit(&bar_s[j & 1]);
+      }
+      __syncwarp();
+    };
+    issue_s(0);
+    if (ntiles > 1) issue_s(1);
+    for (int j = 0; j < ntiles; ++j) {
+      const int g = j & 1, i = j >> 1;
+      if (j + 2 < ntiles) {
+        mbar_wait(&bar_sfree[g], i & 1);     // group g holds S_j in registers: its S tile may be overwritten
+        issue_s(j + 2);
+      }
+      const int st = j % kSplitStages;
+      mbar_wait(&full_v[st], (j / kSplitStages) & 1);
+      mbar_wait(&bar_p[g], i & 1);
+      tc_fence_after();
+      const uint32_t aP = smem_u32(sP + g * kAtomBytes);
+      const uint32_t aV = smem_u32(sV + st * kKvTileBytes);
+      if (elect_one()) {
+#pragma unroll
+        for (int k16 = 0; k16 < 4; ++k16)
+          umma_f16_ss(tmem_base + 128 + (uint32_t)g * 64, make_desc_k_sw128(aP + (uint32_t)k16 * 32),
+                      make_desc_mn_sw128(aV + (uint32_t)k16 * 2048, kKvTileBytes), idesc_o, (i | k16) != 0);
+        umma_commit(&empty_v[st]);
+        umma_commit(&bar_pv[g]);
+      }
+      __syncwarp();
+    }
+  } else {
+    const int qd = warp & 3;
+    const int g = (warp - 2) >> 2;                  // softmax group: KV tiles j = g, g + 2, ...
+    const int row = qd * 32 + lane;
+    const uint32_t lane_off = (uint32_t)(qd * 32) << 16;
+    const uint32_t tmem_S = tmem_base + (uint32_t)g * 64 + lane_off;
+    const uint32_t tmem_O = tmem_base + 128 + (uint32_t)g * 64 + lane_off;
+    const uint32_t a_prow = smem_u32(sP) + (uint32_t)g * kAtomBytes + (uint32_t)row * 128;
+    const uint32_t rx = (uint32_t)(row & 7) << 4;
+    const uint32_t a_bar_s = smem_u32(&bar_s[g]), a_bar_sfree = smem_u32(&bar_sfree[g]), a_bar_pv = smem_u32(&bar_pv[g]),
+                   a_bar_p = smem_u32(&bar_p[g]);
+    const int ng = (ntiles - g + 1) / 2;            // tiles of this group
+    float m = -INFINITY, l = 0.f;
+    const float sl2 = p.scale_log2;
+    for (int i = 0; i < ng; ++i) {
+      const int j = 2 * i + g;
+      const int valid = j < t0 ? min(64, p.nk[0] - j * 64) : min(64, p.nk[1] - (j - t0) * 64);
+      mbar_wait_a(a_bar_s, i & 1);
+      tc_fence_after();
+      uint32_t v[64];
+      tmem_ld32(tmem_S, *reinterpret_cast<uint32_t(*)[32]>(&v[0]));
+      tmem_ld32(tmem_S + 32, *reinterpret_cast<uint32_t(*)[32]>(&v[32]));
+      tmem_ld_wait();
+      tc_fence_before();
+      mbar_arrive_a(a_bar_sfree);
+      if (valid < 64) {
+#pragma unroll
+        for (int c = 0; c < 64; ++c)
+          if (c >= valid) v[c] = 0xff800000u;   // -inf
+      }
+      float mxs[8];
+#pragma unroll
+      for (int c = 0; c < 8; ++c) mxs[c] = __uint_as_float(v[c]);
+#pragma unroll
+      for (int c = 8; c < 64; c += 8) {
+#pragma unroll
+        for (int e = 0; e < 8; ++e) mxs[e] = fmaxf(mxs[e], __uint_as_float(v[c + e]));
+      }
+      const float mx = fmaxf(fmaxf(fmaxf(mxs[0], mxs[1]), fmaxf(mxs[2], mxs[3])),
+                             fmaxf(fmaxf(mxs[4], mxs[5]), fmaxf(mxs[6], mxs[7]))) * sl2;
+      const bool need = mx > m + 8.f;      // lazy rescale: P stays below 2^8, far inside fp16 range
+      float alpha = 1.f;
+      if (need) { alpha = fast_exp2(m - mx); m = mx; }
+      if (i > 0) {
+        mbar_wait_a(a_bar_pv, (i - 1) & 1);  // P_g free again and O_g final before it is rescaled
+        tc_fence_after();
+        if (__any_sync(0xffffffffu, need)) {
+          for (int c0 = 0; c0 < p.dp; c0 += 16) {
+            uint32_t o[16];
+            tmem_ld16(tmem_O + c0, o);
+            tmem_ld_wait();
+#pragma unroll
+            for (int e = 0; e < 16; ++e) o[e] = __float_as_uint(__uint_as_float(o[e]) * alpha);
+            tmem_st16(tmem_O + c0, o);
+          }
+          tmem_st_wait();
+        }
+      }
+      const F2 sl2x2 = f2_make(sl2, sl2), nmx2 = f2_make(-m, -m);
+      float ls0 = 0.f, ls1 = 0.f;
+#pragma unroll
+      for (int c = 0; c < 8; ++c) {   // 8 chunks of 8 keys = one 16-byte smem store each
+        uint32_t ph[4];
+#pragma unroll
+        for (int e = 0; e < 4; ++e) {
+          const int pi = c * 4 + e;
+          float a0, a1;
+          f2_get(f2_fma(f2_make(__uint_as_float(v[2 * pi]), __uint_as_float(v[2 * pi + 1])), sl2x2, nmx2), a0, a1);
+          float p0, p1;
+          if (((pi * kPolyOf8) & 7) < kPolyOf8) {
+            poly_exp2_pair(a0, a1, p0, p1);
+          } else {
+            p0 = fast_exp2(a0);
+            p1 = fast_exp2(a1);
+          }
+          const __half2 hp = __floats2half2_rn(p0, p1);
+          ph[e] = *reinterpret_cast<const uint32_t*>(&hp);
+          if (!kSumInV) {
+            const float2 back = __half22float2(hp);
+            ls0 += back.x; ls1 += back.y;
+          }
+        }
+        sts128(a_prow + (((uint32_t)c << 4) ^ rx), ph[0], ph[1], ph[2], ph[3]);
+      }
+      if (!kSumInV) l = l * alpha + (ls0 + ls1);
+      fence_proxy_async();
+      tc_fence_before();
+      mbar_arrive_a(a_bar_p);
+    }
+    // ---- merge the two groups
+    if (ng > 0) {
+      mbar_wait_a(a_bar_pv, (ng - 1) & 1);
+      tc_fence_after();
+    }
+    if (kSumInV && ng > 0) {
+      // the row sum was accumulated by the tensor core: V carries a column of ones at index d
+      uint32_t o[16];
+      tmem_ld16(tmem_O + (p.d / 16) * 16, o);
+      tmem_ld_wait();
+      l = __uint_as_float(o[p.d % 16 == 8 ? 8 : 0]);
+    }
+    xch[(g * 128 + row) * 2] = m;
+    xch[(g * 128 + row) * 2 + 1] = l;
+    tc_fence_before();
+    named_bar_sync(1, 256);
+    tc_fence_after();
+    const float m_o = xch[((g ^ 1) * 128 + row) * 2], l_o = xch[((g ^ 1) * 128 + row) * 2 + 1];
+    const float mm = fmaxf(m, m_o);
+    const float w_me = fast_exp2(m - mm), w_o = (m_o == -INFINITY) ? 0.f : fast_exp2(m_o - mm);
+    const float wa = g == 0 ? w_me : w_o, wb = g == 0 ? w_o : w_me;     // weights of O_A / O_B
+    const bool has_b = ntiles > 1;
+    const float inv = p.out_scale / (l * w_me + l_o * w_o);
+    const int qrow = q0 + row;
+    const bool ok = qrow < p.Nq;
+    __half* orow = p.out + ((long long)f * p.Nq + qrow) * p.ldo + h * p.d;
+    const uint32_t tmem_OA = tmem_base + 128 + lane_off, tmem_OB = tmem_base + 192 + lane_off;
+    for (int c0 = g * 16; c0 < p.dp; c0 += 32) {    // the two threads of a row split the columns by chunk parity
+      uint32_t oa[16], ob[16];
+      tmem_ld16(tmem_OA + c0, oa);
+      if (has_b) tmem_ld16(tmem_OB + c0, ob);
+      tmem_ld_wait();
+      if (ok) {
+#pragma unroll
+        for (int gg = 0; gg < 2; ++gg) {
+          const int cc = c0 + gg * 8;
+          if (cc < p.d) {
+            __align__(16) __half oh[8];
+            if (p.accumulate) *reinterpret_cast<uint4*>(oh) = *reinterpret_cast<const uint4*>(orow + cc);
+#pragma unroll
+            for (int e = 0; e < 8; ++e) {
+              float x = __uint_as_float(oa[gg * 8 + e]) * wa;
+              if (has_b) x = fmaf(__uint_as_float(ob[gg * 8 + e]), wb, x);
+              x *= inv;
+              if (p.accumulate) x += __half2float(oh[e]);
+              oh[e] = __float2half_rn(x);
+            }
+            *reinterpret_cast<uint4*>(orow + cc) = *reinterpret_cast<const uint4*>(oh);
+          }
+        }
+      }
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) tmem_dealloc(tmem_base, 256u);
+}
+
 cudaError_t launch_attention(cudaStream_t stream, const AttnArgs& a, const char** err) {
   if (a.d % 8 || a.dp % 16 || a.dp < a.d || a.dp > 192 || a.nseg < 1 || a.nseg > 2 || a.heads < 1) {
     *err = "attention: head dim must be a multiple of 8, padded dim a multiple of 16 (<= 192), 1..2 KV segments";
@@ -427,6 +724,32 @@ cudaError_t launch_attention(cudaStream_t stream, const AttnArgs& a, const char*
             p.nk[1], a.accumulate);
   dim3 grid((a.Nq + 127) / 128, a.heads, a.NF);
   ProfScope prof(stream, KC_ATTENTION);
+  // split-KV variant for one-atom head dims: measured 12 % SLOWER than the default kernel at level 0 (3.44 vs 3.06 ms,
+  // DESIGN.md section 7), so it only runs on request (AttnArgs.variant = 2 or env MVB_ATTN=2)
+  static const int attn_env = getenv("MVB_ATTN") ? atoi(getenv("MVB_ATTN")) : 0;
+  if (a.dp <= 64 && (a.variant == 2 || attn_env == 2)) {
+    static bool split_set = false;
+    const int smem_split = kAtomBytes + 2 * kSplitStages * kKvTileBytes + 2 * kAtomBytes + 1024 + 256 + 2048;
+    if (!split_set) {
+      cudaError_t e = cudaFuncSetAttribute(attention_split_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_split);
+      if (e == cudaSuccess)
+        e = cudaFuncSetAttribute(attention_split_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_split);
+      if (e != cudaSuccess) { *err = "cudaFuncSetAttribute(attention_split_kernel)"; return e; }
+      split_set = true;
+    }
+    CUtensorMap sk0, sv0, sk1, sv1;   // 64-key boxes
+    if (!encode_map_2d(&sk0, s0.k, cols, (uint64_t)s0.rows, (uint64_t)s0.ld, 64, 64) ||
+        !encode_map_2d(&sv0, s0.v, cols, (uint64_t)s0.rows, (uint64_t)s0.ld, 64, 64) ||
+        !encode_map_2d(&sk1, s1.k, cols, (uint64_t)s1.rows, (uint64_t)s1.ld, 64, 64) ||
+        !encode_map_2d(&sv1, s1.v, cols, (uint64_t)s1.rows, (uint64_t)s1.ld, 64, 64)) {
+      *err = "cuTensorMapEncodeTiled(K/V, 64-key box) failed"; return cudaErrorInvalidValue;
+    }
+    if (p.sum_in_v) attention_split_kernel<true><<<grid, 320, smem_split, stream>>>(tq, sk0, sv0, sk1, sv1, p);
+    else attention_split_kernel<false><<<grid, 320, smem_split, stream>>>(tq, sk0, sv0, sk1, sv1, p);
+    cudaError_t e2 = cudaGetLastError();
+    if (e2 != cudaSuccess) *err = "attention_split_kernel launch";
+    return e2;
+  }
   kernels[p.sum_in_v ? 1 : 0][poly_idx]<<<grid, 320, smem, stream>>>(tq, tk0, tv0, tk1, tv1, p);
   cudaError_t e = cudaGetLastError();
   if (e != cudaSuccess) *err = "attention_kernel launch";

@@ -33,6 +33,7 @@ struct AttnArgs {
   float out_scale;
   int accumulate;         // out += result
   int v_ones_col;         // every V row holds 1.0 at column h*dp + d (needs dp > d): row sums come from the MMA
+  int variant = 0;        // 0: default kernel, 2: split-KV kernel (dp <= 64)
 };
 
 cudaError_t launch_attention(cudaStream_t stream, const AttnArgs& a, const char** err);

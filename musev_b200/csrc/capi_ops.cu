@@ -66,7 +66,7 @@ int mvb_op_attention(const mvb_attention_desc* d, void* stream) {
     a.seg[s].rows = d->kv_rows[s]; a.seg[s].nk = d->nk[s]; a.seg[s].fdiv = d->fdiv[s]; a.seg[s].fmul = d->fmul[s];
     a.seg[s].fadd = d->fadd[s];
   }
-  a.out = (__half*)d->out; a.ldo = d->ldo; a.out_scale = d->out_scale; a.accumulate = d->accumulate; a.v_ones_col = d->v_ones_col;
+  a.out = (__half*)d->out; a.ldo = d->ldo; a.out_scale = d->out_scale; a.accumulate = d->accumulate; a.v_ones_col = d->v_ones_col; a.variant = d->variant;
   const char* err = nullptr;
   cudaError_t e = launch_attention((cudaStream_t)stream, a, &err);
   if (e != cudaSuccess) return fail(err, e);

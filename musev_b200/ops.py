@@ -82,7 +82,7 @@ def conv_gemm(
     return out
 
 
-def attention(q, segs, NF, Nq, heads, d, dp, scale, out=None, out_scale=1.0, accumulate=False, v_ones_col=False):
+def attention(q, segs, NF, Nq, heads, d, dp, scale, out=None, out_scale=1.0, accumulate=False, v_ones_col=False, variant=0):
     """q: [NF*Nq, >=heads*dp] fp16 (row stride taken from the tensor); segs: list of dicts
     {k, v, nk, fdiv, fmul, fadd} with k/v [rows, >=heads*dp] views sharing a row stride."""
     assert q.dtype == torch.float16 and q.stride(1) == 1
@@ -98,6 +98,7 @@ def attention(q, segs, NF, Nq, heads, d, dp, scale, out=None, out_scale=1.0, acc
         a.nk[i], a.fdiv[i], a.fmul[i], a.fadd[i] = s["nk"], s.get("fdiv", 1), s.get("fmul", s["nk"]), s.get("fadd", 0)
     a.out, a.ldo, a.out_scale, a.accumulate = out.data_ptr(), out.stride(0), out_scale, int(accumulate)
     a.v_ones_col = int(v_ones_col)
+    a.variant = int(variant)
     _capi.check(_capi.lib().mvb_op_attention(C.byref(a), _stream()))
     return out
 

@@ -142,8 +142,10 @@ def test_temporal_attention(ops, B, T, HW, d):
                                                     (4, 2, 256, 40, True, True), (4, 2, 256, 80, True, False),
                                                     (4, 2, 64, 160, True, False), (2, 1, 200, 40, False, True),
                                                     (2, 1, 16, 16, False, False), (6, 3, 1024, 40, True, True)])
-def test_spatial_attention(ops, NF, T, Nq, d, viscond, ones):
-    """Reference-only self attention: K/V = own frame (+) first frame of the batch (attention_processor.py:431-493)."""
+@pytest.mark.parametrize("variant", [0, 2])
+def test_spatial_attention(ops, NF, T, Nq, d, viscond, ones, variant):
+    """Reference-only self attention: K/V = own frame (+) first frame of the batch (attention_processor.py:431-493).
+    variant 2 = the split-KV kernel (taken for padded head dims <= 64, otherwise the default kernel runs)."""
     torch.manual_seed(8)
     heads, dp, M = 8, (d + 15) // 16 * 16, NF * Nq
     q, k, v = (torch.randn(M, heads * d, device=dev).half() for _ in range(3))
@@ -152,7 +154,7 @@ def test_spatial_attention(ops, NF, T, Nq, d, viscond, ones):
     segs = [dict(k=qkv[:, hd:2 * hd], v=qkv[:, 2 * hd:], nk=Nq, fdiv=1, fmul=Nq, fadd=0)]
     if viscond:
         segs.append(dict(k=qkv[:, hd:2 * hd], v=qkv[:, 2 * hd:], nk=Nq, fdiv=T, fmul=T * Nq, fadd=0))
-    out = ops.attention(qkv[:, :hd], segs, NF, Nq, heads, d, dp, d ** -0.5, v_ones_col=ones)
+    out = ops.attention(qkv[:, :hd], segs, NF, Nq, heads, d, dp, d ** -0.5, v_ones_col=ones, variant=variant)
     qf, kf, vf = (t.float().view(NF, Nq, heads, d).permute(0, 2, 1, 3) for t in (q, k, v))
     if viscond:
         idx = (torch.arange(NF, device=dev) // T) * T

@@ -174,3 +174,46 @@ def test_full_size_properties(built_lib):
     assert torch.equal(a, b) and torch.isfinite(a).all() and 0.2 < a.float().std().item() < 2.0
     c = model(x.flip(0), 601, enc.flip(0), **kw).sample
     assert (c.flip(0).float() - a.float()).abs().max().item() < 2e-3
+
+
+def test_full_size_vs_eager_fp16_and_timing(built_lib):
+    """Config-2 shape, full width: the engine against the oracle run the way the reference runs in production -- plain
+    PyTorch fp16 on the same GPU (cuDNN / cuBLAS / SDPA flash kernels). Checks parity at the full size (both sides carry
+    fp16 rounding, so the bound is looser than FWD_TOL) and records the eager time next to the engine time: the
+    practical "beat this" number of SURVEY.md section 8(d). The timing line goes to stdout and gpurun_out/."""
+    import json, os
+    from musev_b200.unet import UNet3DConditionModel
+    from oracle.unet3d_oracle import UNet3DOracle
+    cfg = preset_config("musev")
+    sd16 = make_state_dict(cfg, seed=0, dtype=torch.float16)
+    model = UNet3DConditionModel(cfg, device=dev, dtype=torch.float16)
+    model.load_state_dict(sd16)
+    oracle = UNet3DOracle(cfg, sd16, device=dev, dtype=torch.float16)
+    del sd16
+    inp = make_inputs(cfg, batch=2, frames=16, h=64, w=64, n_vis_cond=1)
+    x, enc = inp["sample"].to(dev).half(), inp["encoder_hidden_states"].to(dev).half()
+    kw = dict(sample_index=inp["sample_index"], vision_conditon_frames_sample_index=inp["vision_conditon_frames_sample_index"], sample_frame_rate=8)
+
+    def timed(fn, iters=3):
+        fn(); torch.cuda.synchronize()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(iters):
+            out = fn()
+        e1.record(); torch.cuda.synchronize()
+        return out, e0.elapsed_time(e1) / iters
+
+    with torch.no_grad():
+        got, ms_engine = timed(lambda: model(x, 601, enc, **kw).sample)
+        ref, ms_eager = timed(lambda: oracle(x, 601, enc, **kw))
+    err = (got.float() - ref.float()).abs().max().item()
+    line = {"shape": "B=2 T=16+1 64x64 musev", "engine_ms": ms_engine, "eager_fp16_torch_ms": ms_eager,
+            "speedup": ms_eager / ms_engine, "max_abs_diff": err}
+    print("EAGER_BASELINE " + json.dumps(line), flush=True)
+    try:
+        os.makedirs("gpurun_out", exist_ok=True)
+        json.dump(line, open("gpurun_out/eager_baseline.json", "w"))
+    except OSError:
+        pass
+    assert torch.isfinite(got).all() and err < 4e-2
+    assert ms_engine < ms_eager
