@@ -8,12 +8,28 @@
 
 namespace mvb {
 
-// x * sigmoid(x) with the two SFU approximations (ex2, rcp): ~1e-6 relative, five instructions
-__device__ __forceinline__ float silu_f(float x) { return __fdividef(x, 1.f + __expf(-x)); }
+// x * sigmoid(x) with the two SFU approximations (ex2.approx.ftz, rcp.approx.ftz): ~1e-6 relative, five instructions
+// (__expf without -ftz adds a denormal-range fix-up of three more)
+__device__ __forceinline__ float silu_f(float x) {
+  float e, r;
+  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(e) : "f"(x * -1.4426950408889634f));
+  asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(1.f + e));
+  return x * r;
+}
 
 struct alignas(16) Half8 {
   __half2 h[4];
 };
+// explicit 128-bit accesses: a plain struct copy of Half8 is compiled to four 32-bit loads / stores, which quadruples
+// the L1 sector traffic and pins every streaming kernel at ~3.3 TB/s (ncu: l1tex throughput 93 %)
+__device__ __forceinline__ Half8 ld_half8(const __half* p) {
+  Half8 r;
+  *reinterpret_cast<uint4*>(&r) = __ldg(reinterpret_cast<const uint4*>(p));
+  return r;
+}
+__device__ __forceinline__ void st_half8(__half* p, const Half8& v) {
+  *reinterpret_cast<uint4*>(p) = *reinterpret_cast<const uint4*>(&v);
+}
 
 // ------------------------------------------------------------------------------------------------ GroupNorm
 // grid (chunks, NF); block 256. Thread owns a fixed 8-channel vector column and strides over pixels, so its
@@ -47,7 +63,7 @@ gn_stats_kernel(const __half* __restrict__ x0, int C0, const __half* __restrict_
       for (; p + 3 * rows_per_iter < p_end; p += 4 * rows_per_iter) {
         Half8 hv[4];
 #pragma unroll
-        for (int u = 0; u < 4; ++u) hv[u] = *reinterpret_cast<const Half8*>(src + (size_t)(p + u * rows_per_iter) * ld);
+        for (int u = 0; u < 4; ++u) hv[u] = ld_half8(src + (size_t)(p + u * rows_per_iter) * ld);
 #pragma unroll
         for (int u = 0; u < 4; ++u)
 #pragma unroll
@@ -58,7 +74,7 @@ gn_stats_kernel(const __half* __restrict__ x0, int C0, const __half* __restrict_
           }
       }
       for (; p < p_end; p += rows_per_iter) {
-        const Half8 hv = *reinterpret_cast<const Half8*>(src + (size_t)p * ld);
+        const Half8 hv = ld_half8(src + (size_t)p * ld);
 #pragma unroll
         for (int j = 0; j < 4; ++j) {
           const float2 t = __half22float2(hv.h[j]);
@@ -93,7 +109,7 @@ cudaError_t gn_stats(cudaStream_t s, const __half* x0, int C0, const __half* x1,
   if ((C0 % 8) || (C1 % 8) || (C % G) || ((C / G) % 2)) return cudaErrorInvalidValue;
   const int threads = 256;
   // ~8 resident blocks per SM (the kernel is latency-bound below that), at least ~32 pixels per block
-  int chunks = (8 * 148 + NF - 1) / NF;
+  int chunks = (8 * 148) / NF;          // rounded down: one full wave
   const int maxc = HW / 32 > 0 ? HW / 32 : 1;
   if (chunks > maxc) chunks = maxc;
   if (chunks > kGnMaxChunks) chunks = kGnMaxChunks;
@@ -150,16 +166,24 @@ gn_apply_kernel(const __half* __restrict__ x0, int C0, const __half* __restrict_
   const int p1 = min(HW, p0 + pix_per_block);
   const int total = (p1 - p0) * vecs;
   // a thread keeps the same channel vector when blockDim is a multiple of vecs; the affine terms are then loaded once
-  const bool fixed_col = (blockDim.x % vecs) == 0;
+  const bool fixed_col = (blockDim.x % vecs) == 0 && cpg >= 8;
   float ga[8], be[8];
   if (fixed_col) {
+    // 8 consecutive channels touch at most two groups (cpg >= 8 whenever this path is taken): one division per thread
     const int c = (threadIdx.x % vecs) * 8;
+    const int g0 = c / cpg;
+    const int edge = (g0 + 1) * cpg;
+    const float4 gm0 = __ldg(reinterpret_cast<const float4*>(gamma + c)), gm1 = __ldg(reinterpret_cast<const float4*>(gamma + c) + 1);
+    const float4 bt0 = __ldg(reinterpret_cast<const float4*>(beta + c)), bt1 = __ldg(reinterpret_cast<const float4*>(beta + c) + 1);
+    const float gmv[8] = {gm0.x, gm0.y, gm0.z, gm0.w, gm1.x, gm1.y, gm1.z, gm1.w};
+    const float btv[8] = {bt0.x, bt0.y, bt0.z, bt0.w, bt1.x, bt1.y, bt1.z, bt1.w};
+    const int g1 = min(g0 + 1, G - 1);
+    const float mean0 = sm_gn[g0], rstd0 = sm_gn[G + g0], mean1 = sm_gn[g1], rstd1 = sm_gn[G + g1];
 #pragma unroll
     for (int j = 0; j < 8; ++j) {
-      const int g = (c + j) / cpg;
-      const float rstd = sm_gn[G + g];
-      ga[j] = rstd * __ldg(gamma + c + j);
-      be[j] = __ldg(beta + c + j) - sm_gn[g] * ga[j];
+      const bool hi = c + j >= edge;
+      ga[j] = (hi ? rstd1 : rstd0) * gmv[j];
+      be[j] = btv[j] - (hi ? mean1 : mean0) * ga[j];
     }
   }
   if (fixed_col) {
@@ -171,7 +195,7 @@ gn_apply_kernel(const __half* __restrict__ x0, int C0, const __half* __restrict_
     __half* dst = y + (size_t)f * HW * C + c;
 #pragma unroll 2
     for (int p = p0 + threadIdx.x / vecs; p < p1; p += rstep) {
-      const Half8 hv = *reinterpret_cast<const Half8*>(src + (size_t)p * ld);
+      const Half8 hv = ld_half8(src + (size_t)p * ld);
       Half8 ov;
 #pragma unroll
       for (int j = 0; j < 4; ++j) {
@@ -181,7 +205,7 @@ gn_apply_kernel(const __half* __restrict__ x0, int C0, const __half* __restrict_
         if (silu) { t.x = silu_f(t.x); t.y = silu_f(t.y); }
         ov.h[j] = __floats2half2_rn(t.x, t.y);
       }
-      *reinterpret_cast<Half8*>(dst + (size_t)p * C) = ov;
+      st_half8(dst + (size_t)p * C, ov);
     }
     return;
   }
@@ -189,7 +213,7 @@ gn_apply_kernel(const __half* __restrict__ x0, int C0, const __half* __restrict_
     const int p = p0 + i / vecs;
     const int c = (i % vecs) * 8;
     const __half* src = (c < C0) ? x0 + ((size_t)f * HW + p) * C0 + c : x1 + ((size_t)f * HW + p) * C1 + (c - C0);
-    const Half8 hv = *reinterpret_cast<const Half8*>(src);
+    const Half8 hv = ld_half8(src);
     Half8 ov;
 #pragma unroll
     for (int j = 0; j < 4; ++j) {
@@ -207,7 +231,7 @@ gn_apply_kernel(const __half* __restrict__ x0, int C0, const __half* __restrict_
       if (silu) { t.x = silu_f(t.x); t.y = silu_f(t.y); }
       ov.h[j] = __floats2half2_rn(t.x, t.y);
     }
-    *reinterpret_cast<Half8*>(y + ((size_t)f * HW + p) * C + c) = ov;
+    st_half8(y + ((size_t)f * HW + p) * C + c, ov);
   }
 }
 
@@ -227,10 +251,13 @@ cudaError_t gn_apply(cudaStream_t s, const __half* x0, int C0, const __half* x1,
   int threads = 256;
   if (vecs <= 256 && (256 % vecs) != 0) threads = (256 / vecs) * vecs;   // e.g. C=320: 240 threads, C=960: 240
   if (threads < 64) threads = 256;
-  int ppb = (32768 + C - 1) / C;
-  if (ppb < 1) ppb = 1;
+  // ~4 waves of 6 resident blocks per SM (a 1.5-wave grid leaves half the machine idle for the second half), at least
+  // 4 rows per thread so that the per-block prologue stays small
+  const int rows_per_pass = threads / (vecs < threads ? vecs : threads) > 0 ? threads / (vecs < threads ? vecs : threads) : 1;
+  int ppb = (int)(((long long)HW * NF + 148 * 24 - 1) / (148 * 24));
+  if (ppb < 4 * rows_per_pass) ppb = 4 * rows_per_pass;
+  if (ppb > HW) ppb = HW;
   int blocks = (HW + ppb - 1) / ppb;
-  while (blocks * NF < 2 * 148 && ppb > 1) { ppb = (ppb + 1) / 2; blocks = (HW + ppb - 1) / ppb; }
   gn_apply_kernel<<<dim3(blocks, NF), threads, 2 * G * sizeof(float), s>>>(x0, C0, x1, C1, HW, G, stats, fps, gamma, beta,
                                                                            silu, y, ppb);
   return cudaGetLastError();
@@ -252,7 +279,7 @@ layernorm_kernel(const __half* __restrict__ x, long long M, int C, float eps, co
 #pragma unroll
     for (int i = 0; i < VPL; ++i) {
       const int vi = lane + i * 32;
-      if (vi < vecs && row0 + r < M) hv[r][i] = *reinterpret_cast<const Half8*>(x + (row0 + r) * C + vi * 8);
+      if (vi < vecs && row0 + r < M) hv[r][i] = ld_half8(x + (row0 + r) * C + vi * 8);
     }
   }
 #pragma unroll
@@ -300,7 +327,7 @@ layernorm_kernel(const __half* __restrict__ x, long long M, int C, float eps, co
         ov.h[1] = __floats2half2_rn((v[i][2] - mean) * rstd * g0.z + b0.z, (v[i][3] - mean) * rstd * g0.w + b0.w);
         ov.h[2] = __floats2half2_rn((v[i][4] - mean) * rstd * g1.x + b1.x, (v[i][5] - mean) * rstd * g1.y + b1.y);
         ov.h[3] = __floats2half2_rn((v[i][6] - mean) * rstd * g1.z + b1.z, (v[i][7] - mean) * rstd * g1.w + b1.w);
-        *reinterpret_cast<Half8*>(y + (row0 + r) * C + vi * 8) = ov;
+        st_half8(y + (row0 + r) * C + vi * 8, ov);
       }
     }
   }
@@ -330,7 +357,7 @@ layernorm40_kernel(const __half* __restrict__ x, long long M, float eps, const f
     Half8 hv[5];
 #pragma unroll
     for (int i = 0; i < 5; ++i)
-      hv[i] = ok ? *reinterpret_cast<const Half8*>(x + row * C + (lr + L * i) * 8) : Half8{};
+      hv[i] = ok ? ld_half8(x + row * C + (lr + L * i) * 8) : Half8{};
     float v[5][8];
     float s0 = 0.f, s1 = 0.f;
 #pragma unroll
@@ -369,7 +396,7 @@ layernorm40_kernel(const __half* __restrict__ x, long long M, float eps, const f
         ov.h[1] = __floats2half2_rn(fmaf(fmaf(v[i][2], rstd, nmr), g0.z, b0.z), fmaf(fmaf(v[i][3], rstd, nmr), g0.w, b0.w));
         ov.h[2] = __floats2half2_rn(fmaf(fmaf(v[i][4], rstd, nmr), g1.x, b1.x), fmaf(fmaf(v[i][5], rstd, nmr), g1.y, b1.y));
         ov.h[3] = __floats2half2_rn(fmaf(fmaf(v[i][6], rstd, nmr), g1.z, b1.z), fmaf(fmaf(v[i][7], rstd, nmr), g1.w, b1.w));
-        *reinterpret_cast<Half8*>(y + row * C + c) = ov;
+        st_half8(y + row * C + c, ov);
       }
     }
   }
@@ -410,8 +437,8 @@ __global__ void upsample2x_kernel(const __half* __restrict__ x, int H, int W, in
     const int ox = (int)(p % (2 * W)); p /= (2 * W);
     const int oy = (int)(p % (2 * H));
     const long long f = p / (2 * H);
-    const Half8 hv = *reinterpret_cast<const Half8*>(x + (((size_t)f * H + oy / 2) * W + ox / 2) * C + v * 8);
-    *reinterpret_cast<Half8*>(y + i * 8) = hv;
+    const Half8 hv = ld_half8(x + (((size_t)f * H + oy / 2) * W + ox / 2) * C + v * 8);
+    st_half8(y + i * 8, hv);
   }
 }
 cudaError_t upsample2x(cudaStream_t s, const __half* x, int NF, int H, int W, int C, __half* y) {
@@ -426,12 +453,12 @@ cudaError_t upsample2x(cudaStream_t s, const __half* x, int NF, int H, int W, in
 __global__ void add_kernel(const __half* __restrict__ a, const __half* __restrict__ b, long long nvec,
                            __half* __restrict__ y) {
   for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < nvec; i += (long long)gridDim.x * blockDim.x) {
-    const Half8 x = reinterpret_cast<const Half8*>(a)[i];
-    const Half8 z = reinterpret_cast<const Half8*>(b)[i];
+    const Half8 x = ld_half8(a + i * 8);
+    const Half8 z = ld_half8(b + i * 8);
     Half8 o;
 #pragma unroll
     for (int j = 0; j < 4; ++j) o.h[j] = __hadd2(x.h[j], z.h[j]);
-    reinterpret_cast<Half8*>(y)[i] = o;
+    st_half8(y + i * 8, o);
   }
 }
 cudaError_t add_tensors(cudaStream_t s, const __half* a, const __half* b, long long n, __half* y) {
