@@ -668,24 +668,28 @@ temporal_attention_mma_kernel(const __half* __restrict__ qkv, int ld, int B, int
   const long long bp = prob / heads;
   const int pix = (int)(bp % HW);
   const int b = (int)(bp / HW);
-  __half* sq = sm_tm + (size_t)warp * 3 * 32 * DS;
-  __half* sk = sq + 32 * DS;
-  __half* sv = sk + 32 * DS;
+  // only T rows (+ one row of zeros that every padded row index is clamped to) are staged per operand: the smem
+  // footprint, not registers, bounds the resident warps, and the kernel is latency-bound (one problem per warp)
+  const int R = T + 1;
+  __half* sq = sm_tm + (size_t)warp * 3 * R * DS;
+  __half* sk = sq + R * DS;
+  __half* sv = sk + R * DS;
   const int hd = heads * DP;
-  for (int i = lane; i < 32 * D8; i += 32) {
+  for (int i = lane; i < R * D8; i += 32) {
     const int t = i / D8, v8 = i % D8;
     uint4 q4 = make_uint4(0, 0, 0, 0), k4 = q4, v4 = q4;
     if (t < T) {
       const __half* row = qkv + (((size_t)b * T + t) * HW + pix) * ld + h * DP + v8 * 8;
-      q4 = *reinterpret_cast<const uint4*>(row);
-      k4 = *reinterpret_cast<const uint4*>(row + hd);
-      v4 = *reinterpret_cast<const uint4*>(row + 2 * hd);
+      q4 = __ldg(reinterpret_cast<const uint4*>(row));
+      k4 = __ldg(reinterpret_cast<const uint4*>(row + hd));
+      v4 = __ldg(reinterpret_cast<const uint4*>(row + 2 * hd));
     }
     *reinterpret_cast<uint4*>(sq + t * DS + v8 * 8) = q4;
     *reinterpret_cast<uint4*>(sk + t * DS + v8 * 8) = k4;
     *reinterpret_cast<uint4*>(sv + t * DS + v8 * 8) = v4;
   }
   __syncwarp();
+  auto rowc = [&](int r) { return r < T ? r : T; };   // padded rows read the zero row
   // ---- S = Q K^T (32 x 32)
   float sacc[2][4][4];
 #pragma unroll
@@ -698,10 +702,10 @@ temporal_attention_mma_kernel(const __half* __restrict__ qkv, int ld, int B, int
   for (int ks = 0; ks < DP / 16; ++ks) {
     uint32_t a[2][4], bk[2][4];
 #pragma unroll
-    for (int mt = 0; mt < 2; ++mt) ldsm_x4(a[mt], sq + (mt * 16 + (lane & 15)) * DS + ks * 16 + (lane >> 4) * 8);
+    for (int mt = 0; mt < 2; ++mt) ldsm_x4(a[mt], sq + rowc(mt * 16 + (lane & 15)) * DS + ks * 16 + (lane >> 4) * 8);
 #pragma unroll
     for (int np = 0; np < 2; ++np)   // two key tiles (16 keys) per ldmatrix.x4
-      ldsm_x4(bk[np], sk + (np * 16 + (lane & 7) + ((lane >> 4) << 3)) * DS + ks * 16 + ((lane >> 3) & 1) * 8);
+      ldsm_x4(bk[np], sk + rowc(np * 16 + (lane & 7) + ((lane >> 4) << 3)) * DS + ks * 16 + ((lane >> 3) & 1) * 8);
 #pragma unroll
     for (int mt = 0; mt < 2; ++mt)
 #pragma unroll
@@ -731,7 +735,8 @@ temporal_attention_mma_kernel(const __half* __restrict__ qkv, int ld, int B, int
     for (int nt = 0; nt < 4; ++nt)
 #pragma unroll
       for (int e = 0; e < 4; ++e) {
-        const float pv = exp2f((sacc[mt][nt][e] - mx[e >> 1]) * scale_log2);
+        float pv;   // SFU approximation, flush-to-zero: exp2(-inf) = 0 for the masked keys
+        asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(pv) : "f"((sacc[mt][nt][e] - mx[e >> 1]) * scale_log2));
         sacc[mt][nt][e] = pv;
         sum[e >> 1] += pv;
       }
@@ -739,7 +744,7 @@ temporal_attention_mma_kernel(const __half* __restrict__ qkv, int ld, int B, int
     for (int r = 0; r < 2; ++r) {
       sum[r] += __shfl_xor_sync(0xffffffffu, sum[r], 1);
       sum[r] += __shfl_xor_sync(0xffffffffu, sum[r], 2);
-      inv[mt][r] = 1.f / sum[r];
+      asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(inv[mt][r]) : "f"(sum[r]));
     }
 #pragma unroll
     for (int k2 = 0; k2 < 2; ++k2) {
@@ -763,7 +768,7 @@ temporal_attention_mma_kernel(const __half* __restrict__ qkv, int ld, int B, int
 #pragma unroll
     for (int k2 = 0; k2 < 2; ++k2) {
       uint32_t bv[4];
-      ldsm_x4_trans(bv, sv + (k2 * 16 + (lane & 7) + ((lane >> 3) & 1) * 8) * DS + n0 + (lane >> 4) * 8);
+      ldsm_x4_trans(bv, sv + rowc(k2 * 16 + (lane & 7) + ((lane >> 3) & 1) * 8) * DS + n0 + (lane >> 4) * 8);
 #pragma unroll
       for (int mt = 0; mt < 2; ++mt) {
         mma16816(oacc[mt][0], pa[mt][k2], bv[0], bv[1]);
@@ -776,8 +781,10 @@ temporal_attention_mma_kernel(const __half* __restrict__ qkv, int ld, int B, int
       for (int nt = 0; nt < 2; ++nt) {
         const int col = n0 + nt * 8 + 2 * (lane & 3);
         const int r_lo = mt * 16 + (lane >> 2);
-        *reinterpret_cast<uint32_t*>(sq + r_lo * DS + col) = pack_h2(oacc[mt][nt][0] * inv[mt][0], oacc[mt][nt][1] * inv[mt][0]);
-        *reinterpret_cast<uint32_t*>(sq + (r_lo + 8) * DS + col) = pack_h2(oacc[mt][nt][2] * inv[mt][1], oacc[mt][nt][3] * inv[mt][1]);
+        if (r_lo < T)
+          *reinterpret_cast<uint32_t*>(sq + r_lo * DS + col) = pack_h2(oacc[mt][nt][0] * inv[mt][0], oacc[mt][nt][1] * inv[mt][0]);
+        if (r_lo + 8 < T)
+          *reinterpret_cast<uint32_t*>(sq + (r_lo + 8) * DS + col) = pack_h2(oacc[mt][nt][2] * inv[mt][1], oacc[mt][nt][3] * inv[mt][1]);
       }
   }
   __syncwarp();
@@ -799,11 +806,11 @@ cudaError_t temporal_attention(cudaStream_t s, const __half* qkv, int ld, int B,
   const float sl2 = scale * 1.4426950408889634f;
 #define MVB_TAM(N)                                                                                                  \
   case N: {                                                                                                          \
-    const size_t smem = (size_t)wpb * 3 * 32 * (N + 8) * sizeof(__half);                                             \
-    static bool set##N = false;                                                                                      \
-    if (!set##N) {                                                                                                   \
+    const size_t smem = (size_t)wpb * 3 * (T + 1) * (N + 8) * sizeof(__half);                                        \
+    static size_t set##N = 0;                                                                                        \
+    if (smem > set##N) {                                                                                             \
       cudaFuncSetAttribute(temporal_attention_mma_kernel<N>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem); \
-      set##N = true;                                                                                                 \
+      set##N = smem;                                                                                                 \
     }                                                                                                                \
     temporal_attention_mma_kernel<N><<<blocks, wpb * 32, smem, s>>>(qkv, ld, B, T, HW, heads, d, sl2, out, ldo);    \
     break;                                                                                                           \

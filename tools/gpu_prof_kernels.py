@@ -43,5 +43,9 @@ for _ in range(2):
     ops.groupnorm(x.view(NF, 4096, 320), g, be, groups=32, frames_per_stat=1, silu=True)
     ops.groupnorm(x.view(NF, 4096, 320), g, be, groups=32, frames_per_stat=17, silu=True)
     ops.layernorm(res, g, be, 1e-5)
+# temporal attention at level 0
+qkv_t = torch.randn(2 * 17 * 4096, 3 * 8 * 48, device=dev).half()
+for _ in range(2):
+    ops.temporal_attention(qkv_t, 2, 17, 4096, 8, 40, 48, 40 ** -0.5)
 torch.cuda.synchronize()
 print("done")
