@@ -243,10 +243,17 @@ def main():
             pass
         peak = peaks.get("bf16_tflops_sustained", 1400.0)
         achieved = fl["gemm"] * n_fwd / (gemm_ms * 1e-3) / 1e12 if gemm_ms > 0 else None
+        # DRAM bytes per launch of this kernel from the committed ncu capture of one forward (same shapes as here)
+        traffic, traffic_src = None, None
+        try:
+            tr = json.load(open(os.path.join(ROOT, "profiles", "r01_gemm_dram_traffic.json")))
+            traffic, traffic_src = tr["dram_bytes_per_launch"], "profiles/r01_gemm_dram_traffic.json (ncu dram__bytes_read+write, mean over the 440 GEMM launches of a forward; algorithmic %.0f MB/launch)" % (tr["algorithmic_bytes_per_launch"] / 1e6)
+        except Exception:
+            pass
         roof = {"kernel": "conv_gemm_kernel (tcgen05 implicit-GEMM conv / linear)", "bound": "tensor",
                 "achieved": achieved, "peak": peak, "unit": "TFLOP/s", "frac": achieved / peak if achieved else None,
                 "peak_source": "MEASURED_PEAKS.json bf16_tflops_sustained" if peaks else "fallback 1.4 PFLOP/s sustained",
-                "traffic": None, "launches_per_step": gemm_n, "avg_launch_ms": gemm_ms / max(gemm_n, 1),
+                "traffic": traffic, "traffic_unit": "bytes/launch", "traffic_source": traffic_src, "launches_per_step": gemm_n, "avg_launch_ms": gemm_ms / max(gemm_n, 1),
                 "algorithmic_tflop_per_forward": fl["gemm"] / 1e12,
                 "step_share": {k: round(v["ms"], 2) for k, v in prof.items()}}
 
