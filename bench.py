@@ -149,6 +149,9 @@ def main():
     import torch.distributed as dist
     if world > 1:
         import datetime
+        # the image exports NCCL_DEBUG=VERSION, which makes NCCL print a banner on stdout next to the one JSON line
+        if os.environ.get("NCCL_DEBUG", "").upper() in ("", "VERSION"):
+            os.environ["NCCL_DEBUG"] = "WARN"
         dist.init_process_group("nccl", device_id=dev, timeout=datetime.timedelta(seconds=240))
 
     from musev_b200 import _capi
