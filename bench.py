@@ -146,6 +146,11 @@ def main():
             raise SystemExit(f"--gpus {args.gpus} but WORLD_SIZE={world}: launch with torch.distributed.run")
     torch.cuda.set_device(local)
     dev = torch.device("cuda", local)
+    # stdout carries exactly one JSON line: anything a library prints while the bench runs (NCCL's version banner, ...)
+    # is sent to stderr by pointing fd 1 at fd 2 until the result is ready
+    sys.stdout.flush()
+    saved_stdout = os.dup(1)
+    os.dup2(2, 1)
     import torch.distributed as dist
     if world > 1:
         import datetime
@@ -260,6 +265,9 @@ def main():
                 "algorithmic_tflop_per_forward": fl["gemm"] / 1e12,
                 "step_share": {k: round(v["ms"], 2) for k, v in prof.items()}}
 
+    sys.stdout.flush()
+    os.dup2(saved_stdout, 1)
+    os.close(saved_stdout)
     if rank == 0:
         frames = T * args.steps
         value = frames / (ms_total * 1e-3)
