@@ -1,4 +1,5 @@
-"""Configuration and state-dict schema of the denoiser (names/shapes of `UNet3DConditionModel.state_dict()`).
+"""Configuration and state-dict schema of the denoiser (names/shapes of `UNet3DConditionModel.state_dict()`) and of
+the per-window-step ControlNet encoder that feeds it.
 
 Mirrors what the reference builds in musev/models/unet_3d_condition.py:213-610 for the two released presets
 (musev/models/unet_loader.py:232-268); oracle/make_golden.py checks the generated schema against the
@@ -223,3 +224,87 @@ def refer_emb_shapes(cfg: UNetConfig, h: int, w: int):
             shapes.append((c, hh, ww))
     mid = (boc[-1], hh, ww)
     return shapes, mid
+
+
+# ------------------------------------------------------------------------------------------------ ControlNet (8f-1)
+@dataclass
+class ControlNetConfig:
+    """diffusers `ControlNetModel.__init__` defaults for SD-1.5 ControlNets (models/controlnet.py:181-262)."""
+    in_channels: int = 4
+    conditioning_channels: int = 3
+    block_out_channels: Tuple[int, ...] = (320, 640, 1280, 1280)
+    layers_per_block: int = 2
+    attention_head_dim: int = 8          # number of heads, as in UNetConfig
+    cross_attention_dim: int = 768
+    norm_num_groups: int = 32
+    norm_eps: float = 1e-5
+    conditioning_embedding_out_channels: Tuple[int, ...] = (16, 32, 96, 256)
+    resnet_2d_skip_time_act: bool = False   # lets the oracle reuse the UNet's ResnetBlock2D restatement
+
+    @property
+    def heads(self) -> int:
+        return self.attention_head_dim
+
+    @property
+    def temb_dim(self) -> int:
+        return self.block_out_channels[0] * 4
+
+
+def _vanilla_tfm(prefix: str, C: int, cross_dim: int, out: Dict):
+    out[f"{prefix}.norm.weight"] = (C,)
+    out[f"{prefix}.norm.bias"] = (C,)
+    out[f"{prefix}.proj_in.weight"] = (C, C, 1, 1)
+    out[f"{prefix}.proj_in.bias"] = (C,)
+    _tblock(f"{prefix}.transformer_blocks.0", C, cross_dim, out, ip=False)
+    out[f"{prefix}.proj_out.weight"] = (C, C, 1, 1)
+    out[f"{prefix}.proj_out.bias"] = (C,)
+
+
+def controlnet_param_shapes(cfg: ControlNetConfig) -> "OrderedDict[str, Tuple[int, ...]]":
+    """name -> shape of the reference `ControlNetModel.state_dict()` (diffusers models/controlnet.py:181-447):
+    SD-1.5 encoder half (3 x CrossAttnDownBlock2D + DownBlock2D + UNetMidBlock2DCrossAttn), the conditioning
+    embedding and the 12 + 1 zero convolutions."""
+    out: "OrderedDict[str, Tuple[int, ...]]" = OrderedDict()
+    boc = cfg.block_out_channels
+    c0, temb = boc[0], cfg.temb_dim
+    out["conv_in.weight"] = (c0, cfg.in_channels, 3, 3)
+    out["conv_in.bias"] = (c0,)
+    out["time_embedding.linear_1.weight"] = (temb, c0)
+    out["time_embedding.linear_1.bias"] = (temb,)
+    out["time_embedding.linear_2.weight"] = (temb, temb)
+    out["time_embedding.linear_2.bias"] = (temb,)
+    ce = cfg.conditioning_embedding_out_channels
+    out["controlnet_cond_embedding.conv_in.weight"] = (ce[0], cfg.conditioning_channels, 3, 3)
+    out["controlnet_cond_embedding.conv_in.bias"] = (ce[0],)
+    for i in range(len(ce) - 1):
+        out[f"controlnet_cond_embedding.blocks.{2 * i}.weight"] = (ce[i], ce[i], 3, 3)
+        out[f"controlnet_cond_embedding.blocks.{2 * i}.bias"] = (ce[i],)
+        out[f"controlnet_cond_embedding.blocks.{2 * i + 1}.weight"] = (ce[i + 1], ce[i], 3, 3)
+        out[f"controlnet_cond_embedding.blocks.{2 * i + 1}.bias"] = (ce[i + 1],)
+    out["controlnet_cond_embedding.conv_out.weight"] = (c0, ce[-1], 3, 3)
+    out["controlnet_cond_embedding.conv_out.bias"] = (c0,)
+    nb = len(boc)
+    taps = [c0]                     # channels of the 12 residual taps (conv_in output first)
+    ch = c0
+    for i in range(nb):
+        cin, ch = ch, boc[i]
+        final = i == nb - 1
+        for j in range(cfg.layers_per_block):
+            _resnet(f"down_blocks.{i}.resnets.{j}", cin if j == 0 else ch, ch, temb, out)
+            if not final:
+                _vanilla_tfm(f"down_blocks.{i}.attentions.{j}", ch, cfg.cross_attention_dim, out)
+            taps.append(ch)
+        if not final:
+            out[f"down_blocks.{i}.downsamplers.0.conv.weight"] = (ch, ch, 3, 3)
+            out[f"down_blocks.{i}.downsamplers.0.conv.bias"] = (ch,)
+            taps.append(ch)
+    cm = boc[-1]
+    _resnet("mid_block.resnets.0", cm, cm, temb, out)
+    _vanilla_tfm("mid_block.attentions.0", cm, cfg.cross_attention_dim, out)
+    _resnet("mid_block.resnets.1", cm, cm, temb, out)
+    for k, c in enumerate(taps):
+        out[f"controlnet_down_blocks.{k}.weight"] = (c, c, 1, 1)
+        out[f"controlnet_down_blocks.{k}.bias"] = (c,)
+    out["controlnet_mid_block.weight"] = (cm, cm, 1, 1)
+    out["controlnet_mid_block.bias"] = (cm,)
+    return out

@@ -14,9 +14,11 @@ from typing import Dict, List, Optional, Tuple
 
 import torch
 
-from .schema import UNetConfig, refer_emb_shapes, unet_param_shapes
+from .schema import ControlNetConfig, UNetConfig, controlnet_param_shapes, refer_emb_shapes, unet_param_shapes
 
 _BRANCH_OUT = ("conv2.weight", "proj_out.weight", "to_out.0.weight", "ff.net.2.weight", "conv4.3.weight")
+# the ControlNet's zero-initialised convolutions (controlnet.py:97-99,425-444) are drawn non-zero for the same reason
+_ZERO_INIT = ("controlnet_cond_embedding.conv_out.weight", "controlnet_mid_block.weight")
 
 
 def _gen(seed: int, name: str) -> torch.Generator:
@@ -25,9 +27,11 @@ def _gen(seed: int, name: str) -> torch.Generator:
     return g
 
 
-def make_state_dict(cfg: UNetConfig, seed: int = 0, dtype: torch.dtype = torch.float32) -> "OrderedDict[str, torch.Tensor]":
+def make_state_dict(cfg, seed: int = 0, dtype: torch.dtype = torch.float32) -> "OrderedDict[str, torch.Tensor]":
+    """Seeded weights for a `UNetConfig` (denoiser) or a `ControlNetConfig` (ControlNet encoder)."""
     sd: "OrderedDict[str, torch.Tensor]" = OrderedDict()
-    for name, shape in unet_param_shapes(cfg).items():
+    shapes = controlnet_param_shapes(cfg) if isinstance(cfg, ControlNetConfig) else unet_param_shapes(cfg)
+    for name, shape in shapes.items():
         g = _gen(seed, name)
         if name.endswith("temporal_weight"):
             t = torch.empty(shape).uniform_(0.4, 0.9, generator=g)
@@ -42,7 +46,7 @@ def make_state_dict(cfg: UNetConfig, seed: int = 0, dtype: torch.dtype = torch.f
             fan_in = 1
             for s in shape[1:]:
                 fan_in *= s
-            gain = 0.5 if name.endswith(_BRANCH_OUT) else 1.0
+            gain = 0.5 if (name.endswith(_BRANCH_OUT) or name.endswith(_ZERO_INIT) or name.startswith("controlnet_down_blocks")) else 1.0
             t = torch.randn(shape, generator=g) * (gain / fan_in ** 0.5)
         sd[name] = t.to(dtype)
     return sd
@@ -71,3 +75,17 @@ def make_inputs(cfg: UNetConfig, batch: int, frames: int, h: int, w: int, n_vis_
         out["down_block_refer_embs"] = [r(f"refer{i}", batch, c, n_ref, hh, ww) for i, (c, hh, ww) in enumerate(shapes)]
         out["mid_block_refer_emb"] = r("refer_mid", batch, mid[0], n_ref, mid[1], mid[2])
     return out
+
+
+def make_controlnet_inputs(cfg: ControlNetConfig, frames: int, h: int, w: int, seed: int = 4321) -> Dict[str, object]:
+    """Synthetic call arguments of `ControlNetModel.forward` as `get_controlnet_emb` issues it
+    (musev/pipelines/pipeline_controlnet.py:1238-1262): `sample` is `(b t) c h w`, the prompt embedding is repeated
+    per frame, the condition image is 8x the latent size."""
+    def r(name, *shape, scale=1.0):
+        return torch.randn(*shape, generator=_gen(seed, name)) * scale
+
+    return {
+        "sample": r("cn_sample", frames, cfg.in_channels, h, w),
+        "encoder_hidden_states": r("cn_text", frames, 77, cfg.cross_attention_dim),
+        "controlnet_cond": torch.rand(frames, cfg.conditioning_channels, 8 * h, 8 * w, generator=_gen(seed, "cn_cond")),
+    }

@@ -17,8 +17,8 @@ import torch
 
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, ROOT)
-from musev_b200.schema import preset_config, unet_param_shapes  # noqa: E402
-from musev_b200.synth import make_inputs, make_state_dict  # noqa: E402
+from musev_b200.schema import ControlNetConfig, controlnet_param_shapes, preset_config, unet_param_shapes  # noqa: E402
+from musev_b200.synth import make_controlnet_inputs, make_inputs, make_state_dict  # noqa: E402
 from oracle import ref_shim  # noqa: E402
 from oracle.pipeline_oracle import SD15_DDIM  # noqa: E402
 
@@ -157,19 +157,76 @@ def golden_ddim():
     print("ddim_sd15.pt timesteps", sched.timesteps.tolist())
 
 
+def golden_controlnet(boc, tag, frames, h, w, t, scale, guess, wseed=3, iseed=4321):
+    """The per-window-step ControlNet: the unmodified diffusers `ControlNetModel` of the reference
+    tree, called the way `get_controlnet_emb` calls it (pipeline_controlnet.py:1238-1262). The 13 residual maps are
+    large, so the fixture keeps 512 seeded sample positions + mean / abs-mean of each."""
+    ref_shim.load()
+    from diffusers.models.controlnet import ControlNetModel
+    cfg = ControlNetConfig(block_out_channels=tuple(boc))
+    kw = dict(in_channels=4, conditioning_channels=3, block_out_channels=tuple(boc), layers_per_block=2,
+              cross_attention_dim=768, attention_head_dim=8, norm_num_groups=32,
+              down_block_types=("CrossAttnDownBlock2D", "CrossAttnDownBlock2D", "CrossAttnDownBlock2D", "DownBlock2D"))
+    t0 = time.time()
+    with torch.device("meta"):
+        m = ControlNetModel(**kw)
+    ref_shapes = {k: tuple(v.shape) for k, v in m.state_dict().items()}
+    mine = {k: tuple(v) for k, v in controlnet_param_shapes(cfg).items()}
+    assert ref_shapes == mine, "ControlNet schema mismatch vs reference state_dict"
+    sd = make_state_dict(cfg, seed=wseed)
+    m = m.to_empty(device="cpu")
+    res = m.load_state_dict(sd, strict=True)
+    assert not res.missing_keys and not res.unexpected_keys
+    m.eval()
+    inp = make_controlnet_inputs(cfg, frames=frames, h=h, w=w, seed=iseed)
+    with torch.no_grad():
+        down, mid = m(inp["sample"], torch.tensor(t), inp["encoder_hidden_states"], controlnet_cond=inp["controlnet_cond"],
+                      conditioning_scale=scale, guess_mode=guess, return_dict=False)
+        # second call exactly as the pipeline issues it: the condition embedding computed once, passed as latents
+        cond_lat = m.controlnet_cond_embedding(inp["controlnet_cond"])
+        down2, mid2 = m(inp["sample"], torch.tensor(t), inp["encoder_hidden_states"], controlnet_cond=None,
+                        controlnet_cond_latents=cond_lat, conditioning_scale=scale, guess_mode=guess, return_dict=False)
+    assert all(torch.equal(a, b) for a, b in zip(down, down2)) and torch.equal(mid, mid2)
+    maps = list(down) + [mid]
+    samples, stats = [], []
+    for k, mp in enumerate(maps):
+        flat = mp.reshape(-1)
+        g = torch.Generator().manual_seed(1000 + k)
+        idx = torch.randint(0, flat.numel(), (512,), generator=g)
+        samples.append(flat[idx].clone())
+        stats.append([float(flat.mean()), float(flat.abs().mean())])
+    meta = dict(block_out_channels=list(boc), frames=frames, h=h, w=w, timestep=t, conditioning_scale=scale,
+                guess_mode=guess, weight_seed=wseed, input_seed=iseed, shapes=[list(mp.shape) for mp in maps],
+                sample_seed_base=1000, n_samples=512,
+                source="reference diffusers.models.controlnet.ControlNetModel (vendored fork), CPU fp32")
+    path = os.path.join(GOLDEN, f"controlnet_{tag}.pt")
+    torch.save({"meta": meta, "samples": samples, "stats": stats}, path)
+    print(f"{path}: mid abs-mean {stats[-1][1]:.4f} ({time.time() - t0:.1f}s)", flush=True)
+
+
 if __name__ == "__main__":
     ap = argparse.ArgumentParser()
     ap.add_argument("--full", action="store_true", help="also produce the full-width (1.4 B parameter) fixtures")
+    ap.add_argument("--only", default="", help="'controlnet': regenerate only the ControlNet fixtures")
     args = ap.parse_args()
     os.makedirs(GOLDEN, exist_ok=True)
     torch.set_num_threads(os.cpu_count() or 1)
+    if args.only == "controlnet":
+        golden_controlnet(NARROW, "narrow", frames=3, h=16, w=16, t=601, scale=0.8, guess=False)
+        golden_controlnet(NARROW, "narrow_guess", frames=2, h=8, w=8, t=301, scale=1.0, guess=True)
+        if args.full:
+            golden_controlnet(FULL, "full", frames=2, h=8, w=8, t=601, scale=1.0, guess=False)
+        sys.exit(0)
     golden_contexts()
     golden_ddim()
     for preset in ("musev", "musev_referencenet"):
         m, cfg, sd = golden_unet(preset, NARROW, "narrow", batch=2, frames=4, h=16, w=16, t=601)
         golden_loop(preset, NARROW, "narrow", m, cfg)
         del m, sd
+    golden_controlnet(NARROW, "narrow", frames=3, h=16, w=16, t=601, scale=0.8, guess=False)
+    golden_controlnet(NARROW, "narrow_guess", frames=2, h=8, w=8, t=301, scale=1.0, guess=True)
     if args.full:
         for preset in ("musev", "musev_referencenet"):
             m, cfg, sd = golden_unet(preset, FULL, "full", batch=2, frames=2, h=8, w=8, t=601)
             del m, sd
+        golden_controlnet(FULL, "full", frames=2, h=8, w=8, t=601, scale=1.0, guess=False)

@@ -148,3 +148,33 @@ def test_denoise_loop_oracle_matches_reference(preset):
     assert len(m["contexts"]) >= 3                        # overlapping windows were exercised
     err = (out - g["latents"]).abs().max().item()
     assert err < 2e-4, err
+
+
+# ---- ControlNet encoder: oracle vs the unmodified diffusers ControlNetModel of the reference tree
+@pytest.mark.parametrize("tag", ["narrow", "narrow_guess", "full"])
+def test_controlnet_oracle_matches_reference(tag):
+    from musev_b200.schema import ControlNetConfig, controlnet_param_shapes
+    from musev_b200.synth import make_controlnet_inputs
+    from oracle.controlnet_oracle import ControlNetOracle
+    g = torch.load(os.path.join(GOLDEN, f"controlnet_{tag}.pt"))
+    m = g["meta"]
+    cfg = ControlNetConfig(block_out_channels=tuple(m["block_out_channels"]))
+    sd = make_state_dict(cfg, seed=m["weight_seed"])
+    assert set(sd) == set(controlnet_param_shapes(cfg))
+    oracle = ControlNetOracle(cfg, sd)
+    inp = make_controlnet_inputs(cfg, frames=m["frames"], h=m["h"], w=m["w"], seed=m["input_seed"])
+    down, mid = oracle(inp["sample"], m["timestep"], inp["encoder_hidden_states"], controlnet_cond=inp["controlnet_cond"],
+                       conditioning_scale=m["conditioning_scale"], guess_mode=m["guess_mode"])
+    maps = list(down) + [mid]
+    assert [list(t.shape) for t in maps] == m["shapes"]
+    for k, mp in enumerate(maps):
+        flat = mp.reshape(-1)
+        idx = torch.randint(0, flat.numel(), (m["n_samples"],), generator=torch.Generator().manual_seed(m["sample_seed_base"] + k))
+        ref = g["samples"][k]
+        assert (flat[idx] - ref).abs().max().item() < 2e-5 * max(1.0, ref.abs().max().item()), f"map {k}"
+        assert abs(float(flat.mean()) - g["stats"][k][0]) < 1e-5 and abs(float(flat.abs().mean()) - g["stats"][k][1]) < 1e-5
+    # the pipeline passes the condition embedding pre-computed (`controlnet_cond_latents`, pipeline_controlnet.py:1258)
+    lat = oracle.cond_embedding(inp["controlnet_cond"])
+    down2, mid2 = oracle(inp["sample"], m["timestep"], inp["encoder_hidden_states"], controlnet_cond_latents=lat,
+                         conditioning_scale=m["conditioning_scale"], guess_mode=m["guess_mode"])
+    assert torch.equal(mid, mid2) and all(torch.equal(a, b) for a, b in zip(down, down2))
