@@ -191,6 +191,31 @@ int mvb_debug_tap(mvb_handle* h, int i, char* name, int name_cap, const void** p
 
 
 /* ---------------------------------------------------------------------------------------------------------
+ * ControlNet encoder per window-step. Reference: diffusers `ControlNetModel.forward`
+ * (diffusers/src/diffusers/models/controlnet.py:645-852) as `get_controlnet_emb` calls it
+ * (musev/pipelines/pipeline_controlnet.py:1238-1262): frames on the batch axis, the prompt embedding repeated per
+ * frame, the condition embedding pre-computed once per call (`controlnet_cond_latents`, :1258) -- the embedding conv
+ * stack itself (controlnet.py:101-112) is a one-shot on the 512x512 condition image and stays with the caller.
+ * The handle is created with `mvb_create_controlnet` from the same `mvb_config` (UNet-only switches ignored) and fed
+ * with `mvb_load_weight` by the reference names (`controlnet_cond_embedding.*` is not part of it). */
+#define MVB_CONTROLNET_MAX_OUT 13
+typedef struct mvb_controlnet_args {
+  const void* sample; int sample_is_f32;            /* [NF, in_channels, H, W] */
+  int NF, H, W;
+  float timestep;
+  const void* encoder_hidden_states; int ehs_is_f32; int n_text;   /* [NF, n_text, cross_attention_dim] */
+  const void* cond_latents; int cond_is_f32;        /* [NF, block_out_channels[0], H, W] */
+  int n_out;                                        /* 1 + sum over blocks (layers_per_block + has_downsampler) + 1 (mid) */
+  float scales[MVB_CONTROLNET_MAX_OUT];             /* conditioning_scale, times logspace(-1, 0) in guess mode (:826-833) */
+  void* outs[MVB_CONTROLNET_MAX_OUT];               /* down residuals in order, then the mid residual: [NF, C_k, h_k, w_k] */
+  int out_is_f32;
+} mvb_controlnet_args;
+int mvb_create_controlnet(const mvb_config* cfg, int device, mvb_handle** out);
+long long mvb_controlnet_workspace_bytes(mvb_handle* h, const mvb_controlnet_args* args);
+int mvb_controlnet_forward(mvb_handle* h, const mvb_controlnet_args* args, void* workspace, long long workspace_bytes,
+                           void* stream);
+
+/* ---------------------------------------------------------------------------------------------------------
  * Accounting (used by bench.py). category: 0 conv/linear GEMM, 1 spatial attention, 2 temporal attention,
  * 3 GroupNorm, 4 LayerNorm, 5 other; -1 = all. */
 long long mvb_launch_count(int category);

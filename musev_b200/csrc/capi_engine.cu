@@ -31,6 +31,42 @@ int mvb_create(const mvb_config* cfg, int device, mvb_handle** out) {
   return MVB_OK;
 }
 
+static int check_config(const mvb_config* cfg) {
+  if (cfg->num_blocks < 1 || cfg->num_blocks > 4 || cfg->heads < 1 || cfg->norm_num_groups < 1) return MVB_ERR_INVALID;
+  for (int i = 0; i < cfg->num_blocks; ++i) {
+    const int c = cfg->block_out_channels[i];
+    if (c % 64 || c % cfg->heads || (c / cfg->heads) % 8 || c % cfg->norm_num_groups) return MVB_ERR_INVALID;
+  }
+  if (cfg->cross_attention_dim % 64 || cfg->in_channels * 9 > 64) return MVB_ERR_INVALID;
+  return MVB_OK;
+}
+
+int mvb_create_controlnet(const mvb_config* cfg, int device, mvb_handle** out) {
+  if (!cfg || !out) return MVB_ERR_INVALID;
+  if (check_config(cfg) != MVB_OK) return MVB_ERR_INVALID;
+  int n_out = 2;
+  for (int i = 0; i < cfg->num_blocks; ++i) n_out += cfg->layers_per_block + (i == cfg->num_blocks - 1 ? 0 : 1);
+  if (n_out > MVB_CONTROLNET_MAX_OUT) return MVB_ERR_INVALID;
+  mvb::Engine* e = new (std::nothrow) mvb::Engine(*cfg, device, 1);
+  if (!e) return MVB_ERR_STATE;
+  if (e->error()[0]) { delete e; return MVB_ERR_CUDA; }
+  mvb_handle* h = new (std::nothrow) mvb_handle{e};
+  if (!h) { delete e; return MVB_ERR_STATE; }
+  *out = h;
+  return MVB_OK;
+}
+
+long long mvb_controlnet_workspace_bytes(mvb_handle* h, const mvb_controlnet_args* args) {
+  if (!h || !args) return -1;
+  return h->e->controlnet_workspace_bytes(*args);
+}
+
+int mvb_controlnet_forward(mvb_handle* h, const mvb_controlnet_args* args, void* workspace, long long workspace_bytes,
+                           void* stream) {
+  if (!h || !args) return MVB_ERR_INVALID;
+  return h->e->controlnet_forward(*args, workspace, workspace_bytes, (cudaStream_t)stream);
+}
+
 void mvb_destroy(mvb_handle* h) {
   if (!h) return;
   delete h->e;

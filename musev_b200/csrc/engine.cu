@@ -53,8 +53,14 @@ __global__ void set_ones_kernel(float* v_bias, int heads, int d, int dp) {
 }
 
 // ---------------------------------------------------------------------------------------------- construction
-Engine::Engine(const mvb_config& cfg, int device) : cfg_(cfg), device_(device) {
+Engine::Engine(const mvb_config& cfg, int device, int kind) : cfg_(cfg), device_(device), kind_(kind) {
   heads_ = cfg.heads;
+  if (kind_ == 1) {
+    // the encoder half of a plain SD-1.5 UNet: none of the musev switches apply
+    cfg_.need_transformer_in = cfg_.use_anivv1_cfg = cfg_.resnet_2d_skip_time_act = cfg_.keep_vision_condtion = 0;
+    cfg_.need_refer_emb = cfg_.ip_adapter_cross_attn = cfg_.need_t2i_ip_adapter = 0;
+    ln_eps13_ = 1e-5f;
+  }
   cudaSetDevice(device);
   cudaDeviceGetAttribute(&num_sms_, cudaDevAttrMultiProcessorCount, device);
   if (num_sms_ <= 0) num_sms_ = 148;
@@ -236,6 +242,58 @@ void Engine::build_refer(const std::string& p, ReferAttn& r, int C) {
 }
 
 void Engine::build() {
+  if (kind_ == 1) build_controlnet(); else build_unet();
+}
+
+// ControlNetModel.__init__ (diffusers models/controlnet.py:181-447) minus the conditioning embedding (see header)
+void Engine::build_controlnet() {
+  const mvb_config& c = cfg_;
+  const int nb = c.num_blocks;
+  const int c0 = c.block_out_channels[0], temb = 4 * c0;
+  int n_res_c = 2 * c.block_out_channels[nb - 1];
+  for (int i = 0; i < nb; ++i) n_res_c += c.layers_per_block * c.block_out_channels[i];
+  temb_all_ = make_mat(n_res_c, temb, true);
+  temb_total_ = femb_total_ = 0;
+  conv_in_ = make_mat(c0, 64, true);
+  reg_mat("conv_in.weight", conv_in_, 0, c0, 0, 0, 0, c0, c.in_channels * 9, 1, c.in_channels, 9);
+  reg_vec("conv_in.bias", conv_in_.bias, c0, c0);
+  reg_linear("time_embedding.linear_1", time_l1_, temb, c0, true);
+  reg_linear("time_embedding.linear_2", time_l2_, temb, temb, true);
+  down_.resize(nb);
+  std::vector<int> tap_c;
+  tap_c.push_back(c0);
+  int ch = c0;
+  for (int i = 0; i < nb; ++i) {
+    const int cin = ch;
+    ch = c.block_out_channels[i];
+    const bool final = i == nb - 1;
+    Block& b = down_[i];
+    b.layers.resize(c.layers_per_block);
+    const std::string p = "down_blocks." + std::to_string(i);
+    for (int j = 0; j < c.layers_per_block; ++j) {
+      Layer& L = b.layers[j];
+      build_resnet(p + ".resnets." + std::to_string(j), L.res, j == 0 ? cin : ch, ch);
+      L.has_attn = !final;
+      if (L.has_attn) build_spatial(p + ".attentions." + std::to_string(j), L.st, ch);
+      tap_c.push_back(ch);
+    }
+    b.has_sampler = !final;
+    if (!final) {
+      reg_conv(p + ".downsamplers.0.conv", b.sampler, ch, ch, 9);
+      tap_c.push_back(ch);
+    }
+  }
+  const int cm = c.block_out_channels[nb - 1];
+  build_resnet("mid_block.resnets.0", mid_res_[0], cm, cm);
+  build_spatial("mid_block.attentions.0", mid_st_, cm);
+  build_resnet("mid_block.resnets.1", mid_res_[1], cm, cm);
+  n_zero_convs_ = (int)tap_c.size() + 1;
+  for (int k = 0; k < (int)tap_c.size() && k < MVB_CONTROLNET_MAX_OUT - 1; ++k)
+    reg_conv("controlnet_down_blocks." + std::to_string(k), zero_convs_[k], tap_c[k], tap_c[k], 1);
+  reg_conv("controlnet_mid_block", zero_convs_[n_zero_convs_ - 1], cm, cm, 1);
+}
+
+void Engine::build_unet() {
   const mvb_config& c = cfg_;
   const int nb = c.num_blocks;
   const int c0 = c.block_out_channels[0], temb = 4 * c0;
@@ -536,7 +594,7 @@ struct Engine::Fwd {
   // GEGLU feed-forward + residual (diffusers models/attention.py:342-395)
   void feed_forward(const TBlock& b, __half* h, long long M, int C, __half* nbuf) {
     const size_t mk = mark();
-    ln(h, M, C, 0.f, b.n3, nbuf);
+    ln(h, M, C, E->ln_eps13_, b.n3, nbuf);
     __half* ff = alloc_h(M, 4 * C);
     Epilogue e1;
     e1.out = ff; e1.ldc = 4 * C; e1.geglu = 1;
@@ -560,7 +618,7 @@ struct Engine::Fwd {
     // attn1: reference-only self attention
     {
       const size_t mk2 = mark();
-      ln(h, M, C, 0.f, b.n1, nbuf);
+      ln(h, M, C, E->ln_eps13_, b.n1, nbuf);
       __half* qkv = alloc_h(M, 3 * hd);
       { Epilogue ep; ep.out = qkv; ep.ldc = 3 * hd; gemm(nbuf, M, C, b.qkv1, ep, b.qkv1.bias != nullptr); }
       __half* ao = alloc_h(M, C);
@@ -942,7 +1000,147 @@ bool Engine::run(const mvb_unet_args& a, Arena& ar, cudaStream_t s) {
   return f.ok;
 }
 
+// ControlNetModel.forward (diffusers models/controlnet.py:645-852), frames on the batch axis
+bool Engine::run_controlnet(const mvb_controlnet_args& a, Arena& ar, cudaStream_t s) {
+  const mvb_config& c = cfg_;
+  const int nb = c.num_blocks, c0 = c.block_out_channels[0], temb = 4 * c0;
+  const int NF = a.NF;
+  if (NF < 1 || a.H < 1 || a.W < 1) { err_ = "controlnet: bad shape"; return false; }
+  if (a.H % (1 << (nb - 1)) || a.W % (1 << (nb - 1))) { err_ = "H and W must be divisible by 2^(num_blocks-1)"; return false; }
+  if (a.n_out != n_zero_convs_) { err_ = "controlnet: n_out must be the number of residual maps (12 + 1 for SD-1.5)"; return false; }
+  mvb_unet_args ua{};                     // what the shared layer functions read
+  ua.B = NF; ua.T = 1; ua.H = a.H; ua.W = a.W; ua.n_text = a.n_text; ua.n_vis_cond = 0; ua.ip_adapter_scale = 0.f;
+  Fwd f;
+  f.E = this; f.ar = &ar; f.s = s; f.dry = ar.dry; f.a = &ua;
+  f.B = NF; f.T = 1; f.H = a.H; f.W = a.W; f.NF = NF;     // every frame is its own batch element (own text rows)
+  f.heads = heads_;
+  f.skip_temporal = true;
+  f.femb_table = nullptr;
+  f.clip = nullptr;
+  if (!ar.dry) taps_.clear();
+  f.gn_part = f.alloc_f((long long)NF * (kGnMaxChunks + 1) * c.norm_num_groups * 2);
+  // ---- time embedding (:733-741): one timestep for all frames; ResnetBlock2D applies SiLU before time_emb_proj
+  float* temb_table = f.alloc_f((long long)NF * temb_total_);
+  f.temb_table = temb_table;
+  {
+    const size_t mk = f.mark();
+    __half* sin_t = f.alloc_h(1, c0);
+    __half* e1 = f.alloc_h(1, temb);
+    __half* e2 = f.alloc_h(1, temb);
+    __half* temb_rows = f.alloc_h(NF, temb);
+    if (!ar.dry) {
+      float v = a.timestep;
+      cudaMemcpyAsync(fidx_dev_, &v, sizeof(float), cudaMemcpyHostToDevice, s);
+      if (sinusoid(s, fidx_dev_, 1, c0, sin_t, c0) != cudaSuccess) f.fail("sinusoid", cudaGetLastError());
+    }
+    { Epilogue ep; ep.out = e1; ep.ldc = temb; ep.act = 1; f.gemm(sin_t, 1, c0, time_l1_, ep); }
+    { Epilogue ep; ep.out = e2; ep.ldc = temb; f.gemm(e1, 1, temb, time_l2_, ep); }
+    if (!ar.dry && f.ok) {
+      cudaError_t e = expand_rows(s, e2, 1, NF, temb, zero_idx_dev_, 0, 1, temb_rows);
+      if (e != cudaSuccess) f.fail("expand_rows(temb)", e);
+    }
+    { Epilogue ep; ep.out = (__half*)temb_table; ep.ldc = temb_total_; ep.out_f32 = 1; f.gemm(temb_rows, NF, temb, temb_all_, ep); }
+    f.release(mk);
+  }
+  // ---- text tokens: [NF, n_text, X]
+  const int X = c.cross_attention_dim;
+  __half* enc = f.alloc_h((long long)NF * a.n_text, X);
+  if (!ar.dry && f.ok) {
+    cudaError_t e = ncthw_to_tokens(s, a.encoder_hidden_states, a.ehs_is_f32, 1, 1, 1, NF * a.n_text * X, enc, 1, 1.f);
+    if (e != cudaSuccess) f.fail("encoder_hidden_states convert", e);
+  }
+  f.enc = enc;
+  // ---- conv_in + condition embedding (:780-785)
+  int Hc = a.H, Wc = a.W;
+  long long M = (long long)NF * Hc * Wc;
+  __half* x = f.alloc_h(M, c0);
+  {
+    const size_t mk = f.mark();
+    __half* A = f.alloc_h(M, 64);
+    __half* cond = f.alloc_h(M, c0);
+    if (!ar.dry && f.ok) {
+      cudaError_t e = im2col_latent(s, a.sample, a.sample_is_f32, NF, c.in_channels, 1, Hc, Wc, A);
+      if (e == cudaSuccess) e = ncthw_to_tokens(s, a.cond_latents, a.cond_is_f32, NF, c0, 1, Hc * Wc, cond, c0, 1.f);
+      if (e != cudaSuccess) f.fail("controlnet inputs", e);
+    }
+    Epilogue ep; ep.out = x; ep.ldc = c0; ep.res = cond; ep.ld_res = c0;
+    f.gemm(A, M, 64, conv_in_, ep);
+    f.release(mk);
+  }
+  struct TapT { __half* p; int C, H, W; };
+  std::vector<TapT> tp;
+  tp.push_back({x, c0, Hc, Wc});
+  int ch = c0;
+  for (int i = 0; i < nb; ++i) {                                                     // :788-801
+    const bool final = i == nb - 1;
+    Block& blk = down_[i];
+    for (int j = 0; j < c.layers_per_block; ++j) {
+      Layer& L = blk.layers[j];
+      x = f.resnet(L.res, x, ch, nullptr, 0, Hc, Wc);
+      ch = L.res.C;
+      if (L.has_attn) x = f.spatial(L.st, x, Hc * Wc);
+      f.tap("down_blocks." + std::to_string(i) + "." + std::to_string(j), x, (long long)NF * Hc * Wc, ch);
+      tp.push_back({x, ch, Hc, Wc});
+    }
+    if (!final) {
+      __half* y = f.alloc_h((long long)NF * (Hc / 2) * (Wc / 2), ch);
+      if (!ar.dry && f.ok) {
+        Epilogue ep; ep.out = y; ep.ldc = ch; ep.bias = blk.sampler.bias;
+        const char* err = nullptr;
+        cudaError_t e = launch_conv_s2(s, x, ch, Wc, Hc, NF, blk.sampler.w, ch, ep, num_sms_, &err);
+        if (e != cudaSuccess) f.fail(err, e);
+      }
+      x = y; Hc /= 2; Wc /= 2;
+      tp.push_back({x, ch, Hc, Wc});
+    }
+  }
+  x = f.resnet(mid_res_[0], x, ch, nullptr, 0, Hc, Wc);                              // :804-811
+  x = f.spatial(mid_st_, x, Hc * Wc);
+  x = f.resnet(mid_res_[1], x, ch, nullptr, 0, Hc, Wc);
+  f.tap("mid", x, (long long)NF * Hc * Wc, ch);
+  tp.push_back({x, ch, Hc, Wc});
+  if ((int)tp.size() != n_zero_convs_) { err_ = "controlnet: tap count mismatch"; return false; }
+  // ---- zero convolutions and scaling (:815-833)
+  for (int k = 0; k < n_zero_convs_; ++k) {
+    const TapT& t = tp[k];
+    const long long Mk = (long long)NF * t.H * t.W;
+    const size_t mk = f.mark();
+    __half* o = f.alloc_h(Mk, t.C);
+    Epilogue ep; ep.out = o; ep.ldc = t.C; ep.alpha = a.scales[k];
+    f.gemm(t.p, Mk, t.C, zero_convs_[k], ep);
+    if (!ar.dry && f.ok) {
+      if (!a.outs[k]) { err_ = "controlnet: null output pointer"; return false; }
+      cudaError_t e = tokens_to_ncthw(s, o, t.C, NF, t.C, 1, t.H * t.W, a.outs[k], a.out_is_f32);
+      if (e != cudaSuccess) f.fail("controlnet output", e);
+    }
+    f.release(mk);
+  }
+  return f.ok;
+}
+
+long long Engine::controlnet_workspace_bytes(const mvb_controlnet_args& a) {
+  if (kind_ != 1) { err_ = "not a ControlNet handle"; return -1; }
+  Arena ar;
+  ar.dry = true;
+  if (!run_controlnet(a, ar, nullptr)) return -1;
+  return (long long)ar.peak + 4096;
+}
+
+int Engine::controlnet_forward(const mvb_controlnet_args& a, void* workspace, long long wbytes, cudaStream_t stream) {
+  if (kind_ != 1) { err_ = "not a ControlNet handle"; return MVB_ERR_STATE; }
+  if (!finalized_) { err_ = "mvb_finalize has not been called (or weights are missing)"; return MVB_ERR_STATE; }
+  if (!a.sample || !a.cond_latents || !a.encoder_hidden_states || !workspace) { err_ = "null pointer argument"; return MVB_ERR_INVALID; }
+  cudaSetDevice(device_);
+  Arena ar;
+  ar.dry = false;
+  ar.base = (char*)workspace;
+  ar.cap = (size_t)wbytes;
+  if (!run_controlnet(a, ar, stream)) return MVB_ERR_CUDA;
+  return MVB_OK;
+}
+
 long long Engine::workspace_bytes(const mvb_unet_args& a) {
+  if (kind_ != 0) { err_ = "not a UNet handle"; return -1; }
   Arena ar;
   ar.dry = true;
   if (!run(a, ar, nullptr)) return -1;
@@ -950,6 +1148,7 @@ long long Engine::workspace_bytes(const mvb_unet_args& a) {
 }
 
 int Engine::forward(const mvb_unet_args& a, void* workspace, long long wbytes, cudaStream_t stream) {
+  if (kind_ != 0) { err_ = "not a UNet handle"; return MVB_ERR_STATE; }
   if (!finalized_) { err_ = "mvb_finalize has not been called (or weights are missing)"; return MVB_ERR_STATE; }
   if (!a.sample || !a.out || !a.encoder_hidden_states || !workspace) { err_ = "null pointer argument"; return MVB_ERR_INVALID; }
   cudaSetDevice(device_);

@@ -112,12 +112,16 @@ struct Arena {
 
 class Engine {
  public:
-  explicit Engine(const mvb_config& cfg, int device);
+  // kind 0: UNet3DConditionModel; kind 1: ControlNet encoder (diffusers models/controlnet.py)
+  explicit Engine(const mvb_config& cfg, int device, int kind = 0);
   ~Engine();
   int load_weight(const char* name, const void* dev_ptr, int is_f32, const long long* shape, int ndim);
   int finalize();
   long long workspace_bytes(const mvb_unet_args& a);
   int forward(const mvb_unet_args& a, void* workspace, long long workspace_bytes, cudaStream_t stream);
+  long long controlnet_workspace_bytes(const mvb_controlnet_args& a);
+  int controlnet_forward(const mvb_controlnet_args& a, void* workspace, long long workspace_bytes, cudaStream_t stream);
+  int kind() const { return kind_; }
   const char* error() const { return err_.c_str(); }
   struct Tap { std::string name; const __half* p; long long rows; int C; };
   const std::vector<Tap>& taps() const { return taps_; }
@@ -126,6 +130,8 @@ class Engine {
  private:
   // construction
   void build();
+  void build_unet();
+  void build_controlnet();
   template <typename T> T* slab(size_t n);
   Mat make_mat(int N, int K, bool bias);
   Norm make_norm(const std::string& p, int C);
@@ -144,9 +150,12 @@ class Engine {
   // forward helpers (all return false on error, message in err_)
   struct Fwd;
   bool run(const mvb_unet_args& a, Arena& ar, cudaStream_t s);
+  bool run_controlnet(const mvb_controlnet_args& a, Arena& ar, cudaStream_t s);
 
   mvb_config cfg_;
   int device_ = 0, num_sms_ = 148;
+  int kind_ = 0;
+  float ln_eps13_ = 0.f;       // LayerNorm eps of norm1 / norm3: 0 in the musev blocks (Q1), 1e-5 in the vanilla diffusers blocks
   int heads_ = 8;
   bool finalized_ = false;
   std::string err_;
@@ -175,6 +184,8 @@ class Engine {
   TemporalT mid_tt_;
   int* zero_idx_dev_ = nullptr;  // device int[32] scratch for vis-cond frame indices
   float* fidx_dev_ = nullptr;    // device float[64] scratch for timestep / frame index values
+  Mat zero_convs_[MVB_CONTROLNET_MAX_OUT];   // ControlNet: controlnet_down_blocks.* then controlnet_mid_block
+  int n_zero_convs_ = 0;
 };
 
 }  // namespace mvb
