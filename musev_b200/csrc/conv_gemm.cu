@@ -1,13 +1,16 @@
 // tcgen05 / TMA implicit-GEMM kernel. See conv_gemm.cuh for the math and the reference call sites.
 //
-// CTA = 384 threads, persistent over output tiles (128 rows x block_n columns):
+// CTA = 384 threads, persistent over output tiles (128 rows x block_n columns; 256 rows on a CTA pair):
 //   warp 0   : TMA producer  -- per K block (64 channels of one tap) loads the A box {64, bw, bh, bn}
-//              (out-of-image taps are zero-filled by TMA = conv padding) and the weight tile {64, block_n}
-//   warp 1   : MMA issuer    -- one thread issues 4 x tcgen05.mma (K=16 each) per K block into TMEM
+//              (out-of-image taps are zero-filled by TMA = conv padding) and the weight tile {64, block_n};
+//              warp-uniform loop, elect.sync picks the issuing lane (a single-thread loop was the mainloop bottleneck)
+//   warp 1   : MMA issuer    -- 4 x tcgen05.mma (K=16 each) per K block into TMEM, same warp-uniform structure
 //   warp 2   : TMEM allocator (512 columns = 2 accumulator stages x up to 256 fp32 columns)
 //   warps 4-11: epilogue     -- two warps per TMEM lane quarter, alternating 32-column chunks: tcgen05.ld accumulator
-//              rows, bias / time-embedding / residual (prefetched one chunk ahead) / GEGLU, fp16 store
-// Pipelines: smem ring (full/empty mbarriers, 4 stages) and TMEM double buffer (tmem_full/tmem_empty).
+//              rows -> bias / time-embedding / residual / GEGLU (four template variants) -> fp16 -> swizzled smem
+//              staging -> TMA store (4-deep staging ring per column half, one named barrier per chunk)
+// Pipelines: smem operand ring (full/empty mbarriers, 160 KB cut into 3..8 stages per launch) and the TMEM double
+// buffer (tmem_full/tmem_empty). kTwoCta: cluster of 2 with cta_group::2 MMAs (M = 256), used for K >= 1280.
 #include "conv_gemm.cuh"
 
 #include <dlfcn.h>
