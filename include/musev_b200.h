@@ -177,6 +177,17 @@ void mvb_destroy(mvb_handle* h);
 /* Reference: from_pretrained_2d / load_state_dict (unet_3d_condition.py:1284-1637): feed every tensor of the
  * reference state_dict by its reference name; the library packs it into its kernel layout on the device. */
 int mvb_load_weight(mvb_handle* h, const char* name, const void* device_ptr, int is_f32, const long long* shape, int ndim);
+/* Batched form (the `mvb_load_weights(h, const mvb_named_tensor*, n)` of SURVEY.md 8b): every entry is validated, then the
+ * whole batch is packed by one kernel launch; synchronous (the sources may be freed on return). Entries not in a batch can
+ * still be fed through mvb_load_weight; mvb_finalize checks that the union covers the schema. */
+typedef struct mvb_named_tensor {
+  const char* name;          /* reference state_dict key */
+  const void* device_ptr;    /* contiguous tensor on the handle's device */
+  int is_f32;                /* 1: float32, 0: float16 */
+  int ndim;                  /* 0..5 */
+  long long shape[5];
+} mvb_named_tensor;
+int mvb_load_weights(mvb_handle* h, const mvb_named_tensor* tensors, int n);
 /* Checks that every tensor of the schema has been loaded. */
 int mvb_finalize(mvb_handle* h);
 int mvb_num_params(mvb_handle* h);

@@ -22,7 +22,7 @@ import torch.nn.functional as F
 
 from . import _capi
 from .schema import ControlNetConfig, controlnet_param_shapes
-from .unet import MvbConfig, _is_f32, _lib as _unet_lib
+from .unet import MvbConfig, _is_f32, _lib as _unet_lib, load_weights_batched
 
 MAX_OUT = 13
 
@@ -112,6 +112,7 @@ class ControlNetModel:
         if strict and (missing or unexpected):
             raise RuntimeError(f"Error(s) in loading state_dict: missing {missing[:5]} unexpected {unexpected[:5]}")
         l = _lib()
+        todo = []
         for name, shape in expected.items():
             if name not in state_dict:
                 continue
@@ -121,15 +122,8 @@ class ControlNetModel:
             if name.startswith("controlnet_cond_embedding."):
                 self._cond_w[name] = t.to(self.device, self.dtype).contiguous()
                 continue
-            if t.dtype not in (torch.float16, torch.float32):
-                t = t.float()
-            t = t.to(self.device).contiguous()
-            shp = (C.c_longlong * max(1, t.dim()))(*t.shape)
-            rc = l.mvb_load_weight(self._h, name.encode(), t.data_ptr(), _is_f32(t), shp, t.dim())
-            if rc != 0:
-                raise _capi.MvbError(f"mvb_load_weight({name}): {l.mvb_handle_error(self._h).decode()}")
-            torch.cuda.current_stream().synchronize()
-            del t
+            todo.append((name, t))
+        load_weights_batched(self._h, todo, self.device)
         rc = l.mvb_finalize(self._h)
         if rc != 0:
             raise _capi.MvbError(f"mvb_finalize: {l.mvb_handle_error(self._h).decode()}")

@@ -701,7 +701,10 @@ cudaError_t launch_attention(cudaStream_t stream, const AttnArgs& a, const char*
   // share of the exp2 work moved from the SFU to the FMA pipe: 0, 2/8 (default), 3/8 or 4/8 (env MVB_POLY, experiments)
   static const int poly_env = getenv("MVB_POLY") ? atoi(getenv("MVB_POLY")) : 2;
   const int poly_idx = poly_env <= 0 ? 0 : poly_env == 2 ? 1 : poly_env >= 4 ? 3 : 2;
-  static int max_set = 0;
+  static int max_set_dev[64] = {};     // per device (the attribute belongs to the device's context)
+  int cur_dev = 0;
+  cudaGetDevice(&cur_dev);
+  int& max_set = max_set_dev[cur_dev & 63];
   if (smem > max_set) {
     cudaError_t e = cudaSuccess;
     for (int a = 0; a < 2 && e == cudaSuccess; ++a)
@@ -734,7 +737,8 @@ cudaError_t launch_attention(cudaStream_t stream, const AttnArgs& a, const char*
   // DESIGN.md section 7), so it only runs on request (AttnArgs.variant = 2 or env MVB_ATTN=2)
   static const int attn_env = getenv("MVB_ATTN") ? atoi(getenv("MVB_ATTN")) : 0;
   if (a.dp <= 64 && (a.variant == 2 || attn_env == 2)) {
-    static bool split_set = false;
+    static bool split_set_dev[64] = {};
+    bool& split_set = split_set_dev[cur_dev & 63];
     const int smem_split = kAtomBytes + 2 * kSplitStages * kKvTileBytes + 2 * kAtomBytes + 1024 + 256 + 2048;
     if (!split_set) {
       cudaError_t e = cudaFuncSetAttribute(attention_split_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_split);

@@ -78,6 +78,11 @@ int mvb_load_weight(mvb_handle* h, const char* name, const void* device_ptr, int
   return h->e->load_weight(name, device_ptr, is_f32, shape, ndim);
 }
 
+int mvb_load_weights(mvb_handle* h, const mvb_named_tensor* tensors, int n) {
+  if (!h || (!tensors && n > 0) || n < 0) return MVB_ERR_INVALID;
+  return h->e->load_weights(tensors, n);
+}
+
 int mvb_finalize(mvb_handle* h) { return h ? h->e->finalize() : MVB_ERR_INVALID; }
 int mvb_num_params(mvb_handle* h) { return h ? h->e->num_params() : 0; }
 

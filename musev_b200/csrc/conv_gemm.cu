@@ -579,7 +579,11 @@ static cudaError_t launch_common(cudaStream_t stream, const CUtensorMap* maps, i
        conv_gemm_kernel<false, kEpiGeglu>},
       {conv_gemm_kernel<true, kEpiGeneric>, conv_gemm_kernel<true, kEpiPlain>, conv_gemm_kernel<true, kEpiResidual>,
        conv_gemm_kernel<true, kEpiGeglu>}};
-  static bool attr_set = false;
+  // the opt-in is per device: key the "already set" state by the current device ordinal
+  static bool attr_set_dev[64] = {};
+  int cur_dev = 0;
+  cudaGetDevice(&cur_dev);
+  bool& attr_set = attr_set_dev[cur_dev & 63];
   if (!attr_set) {
     for (int a = 0; a < 2; ++a)
       for (int b = 0; b < 4; ++b) {

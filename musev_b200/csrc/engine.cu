@@ -47,9 +47,55 @@ __global__ void pack_vec_kernel(float* __restrict__ dst, int n, const TSrc* __re
   }
 }
 
-__global__ void set_ones_kernel(float* v_bias, int heads, int d, int dp) {
-  const int h = blockIdx.x * blockDim.x + threadIdx.x;
-  if (h < heads) v_bias[h * dp + d] = 1.f;
+struct OnesDesc { float* v_bias; int heads, d, dp; };
+// one launch for every V bias of the model: block b plants the ones column of entry b
+__global__ void set_ones_kernel(const OnesDesc* __restrict__ descs) {
+  const OnesDesc o = descs[blockIdx.x];
+  for (int h = threadIdx.x; h < o.heads; h += blockDim.x) o.v_bias[h * o.dp + o.d] = 1.f;
+}
+
+// Batched packing (mvb_load_weights): one launch packs a whole batch of tensors; blockIdx.y selects the tensor and the
+// blocks of a row grid-stride over its elements. Same index arithmetic as the two single-tensor kernels above.
+struct PackDesc {
+  void* dst; const void* src;
+  long long ld;
+  int rows_dst, kdst, nsrc, ksrc, rowmode, p0, p1, colmode, cin, taps;
+  int is_vec, vn, vmode, is_f32;
+};
+__device__ __forceinline__ float pack_src(const void* src, long long i, int is_f32) {
+  return is_f32 ? reinterpret_cast<const float*>(src)[i] : __half2float(reinterpret_cast<const __half*>(src)[i]);
+}
+__global__ void pack_batch_kernel(const PackDesc* __restrict__ descs) {
+  const PackDesc d = descs[blockIdx.y];
+  if (d.is_vec) {
+    float* dst = reinterpret_cast<float*>(d.dst);
+    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < d.vn; i += gridDim.x * blockDim.x) {
+      int si = i;
+      if (d.vmode == 2) { const int chunk = i / 32, j = i % 32; si = j < 16 ? chunk * 16 + j : d.vn / 2 + chunk * 16 + (j - 16); }
+      dst[i] = (si < d.nsrc) ? pack_src(d.src, si, d.is_f32) : 0.f;
+    }
+    return;
+  }
+  __half* dst = reinterpret_cast<__half*>(d.dst);
+  const long long total = (long long)d.rows_dst * d.kdst;
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+    const int r = (int)(i / d.kdst), kk = (int)(i % d.kdst);
+    int srow = r;
+    if (d.rowmode == 1) {
+      const int h = r / d.p1, j = r % d.p1;
+      srow = j < d.p0 ? h * d.p0 + j : -1;
+    } else if (d.rowmode == 2) {
+      const int chunk = r / 32, j = r % 32;
+      srow = j < 16 ? chunk * 16 + j : d.rows_dst / 2 + chunk * 16 + (j - 16);
+    }
+    int scol = kk;
+    if (d.colmode == 1) {
+      if (kk < d.cin * d.taps) { const int tap = kk / d.cin, c = kk % d.cin; scol = c * d.taps + tap; } else scol = -1;
+    } else if (kk >= d.ksrc) scol = -1;
+    float v = 0.f;
+    if (srow >= 0 && srow < d.nsrc && scol >= 0) v = pack_src(d.src, (long long)srow * d.ksrc + scol, d.is_f32);
+    dst[(long long)r * d.ld + kk] = __float2half_rn(v);
+  }
 }
 
 // ---------------------------------------------------------------------------------------------- construction
@@ -77,7 +123,16 @@ Engine::Engine(const mvb_config& cfg, int device, int kind) : cfg_(cfg), device_
   down_.clear(); up_.clear();
   temb_total_ = femb_total_ = 0;
   build();                                   // pass 2: assign pointers
-  for (const OnesInit& o : ones_init_) set_ones_kernel<<<1, 64>>>(o.v_bias, o.heads, o.d, o.dp);
+  if (!ones_init_.empty()) {
+    std::vector<OnesDesc> od;
+    for (const OnesInit& o : ones_init_) od.push_back({o.v_bias, o.heads, o.d, o.dp});
+    OnesDesc* dd = nullptr;
+    if (cudaMalloc(&dd, od.size() * sizeof(OnesDesc)) == cudaSuccess) {
+      cudaMemcpy(dd, od.data(), od.size() * sizeof(OnesDesc), cudaMemcpyHostToDevice);
+      set_ones_kernel<<<(unsigned)od.size(), 32>>>(dd);
+      cudaFree(dd);    // synchronises with the kernel
+    } else err_ = "cudaMalloc(ones descriptors) failed";
+  }
   cudaMalloc(&zero_idx_dev_, 64 * sizeof(int));
   cudaMalloc(&fidx_dev_, 128 * sizeof(float));
 }
@@ -432,6 +487,62 @@ int Engine::load_weight(const char* name, const void* ptr, int is_f32, const lon
   return MVB_OK;
 }
 
+// Batched form of load_weight: validates every entry first, then packs the whole batch with ONE kernel launch.
+int Engine::load_weights(const mvb_named_tensor* ts, int n) {
+  if (!slab_) { err_ = "engine not initialised"; return MVB_ERR_STATE; }
+  if (n <= 0) return MVB_OK;
+  cudaSetDevice(device_);
+  std::vector<PackDesc> descs;
+  std::vector<Loader*> touched;
+  descs.reserve(n);
+  for (int i = 0; i < n; ++i) {
+    const mvb_named_tensor& t = ts[i];
+    if (!t.name || !t.device_ptr || t.ndim < 0 || t.ndim > 5) { err_ = "mvb_load_weights: bad entry"; return MVB_ERR_INVALID; }
+    auto it = loaders_.find(t.name);
+    if (it == loaders_.end()) { err_ = std::string("unexpected weight name: ") + t.name; return MVB_ERR_INVALID; }
+    Loader& l = it->second;
+    long long numel = 1;
+    for (int k = 0; k < t.ndim; ++k) numel *= t.shape[k];
+    if (l.kind == LK_ABS_SCALAR) {
+      if (numel != 1) { err_ = std::string("bad shape for ") + t.name; return MVB_ERR_INVALID; }
+      float v = 0.f;
+      if (t.is_f32) cudaMemcpy(&v, t.device_ptr, sizeof(float), cudaMemcpyDeviceToHost);
+      else { __half hv; cudaMemcpy(&hv, t.device_ptr, sizeof(__half), cudaMemcpyDeviceToHost); v = __half2float(hv); }
+      *l.host_scalar = fabsf(v);
+      l.loaded = true;
+      continue;
+    }
+    PackDesc d{};
+    d.src = t.device_ptr; d.is_f32 = t.is_f32;
+    if (l.kind == LK_VEC) {
+      if (numel != l.nsrc) { err_ = std::string("bad shape for ") + t.name; return MVB_ERR_INVALID; }
+      d.is_vec = 1; d.dst = l.vdst; d.vn = l.vn; d.nsrc = l.nsrc; d.vmode = l.vmode;
+    } else {
+      if (numel != (long long)l.nsrc * l.ksrc) { err_ = std::string("bad shape for ") + t.name; return MVB_ERR_INVALID; }
+      d.dst = l.dst; d.ld = l.ld; d.rows_dst = l.rows_dst; d.kdst = l.kdst; d.nsrc = l.nsrc; d.ksrc = l.ksrc;
+      d.rowmode = l.rowmode; d.p0 = l.p0; d.p1 = l.p1; d.colmode = l.colmode; d.cin = l.cin; d.taps = l.taps;
+    }
+    descs.push_back(d);
+    touched.push_back(&l);
+  }
+  if (!descs.empty()) {
+    PackDesc* dd = nullptr;
+    if (cudaMalloc(&dd, descs.size() * sizeof(PackDesc)) != cudaSuccess) { err_ = "cudaMalloc(pack descriptors) failed"; return MVB_ERR_CUDA; }
+    cudaMemcpy(dd, descs.data(), descs.size() * sizeof(PackDesc), cudaMemcpyHostToDevice);
+    cudaError_t e = cudaSuccess;
+    for (size_t off = 0; off < descs.size() && e == cudaSuccess; off += 65535) {   // gridDim.y limit
+      const unsigned ny = (unsigned)(descs.size() - off < 65535 ? descs.size() - off : 65535);
+      pack_batch_kernel<<<dim3(96, ny), 256>>>(dd + off);
+      e = cudaGetLastError();
+    }
+    if (e == cudaSuccess) e = cudaDeviceSynchronize();     // the caller may free its source tensors on return
+    cudaFree(dd);
+    if (e != cudaSuccess) { err_ = std::string("pack_batch_kernel: ") + cudaGetErrorString(e); return MVB_ERR_CUDA; }
+  }
+  for (Loader* l : touched) l->loaded = true;
+  return MVB_OK;
+}
+
 int Engine::finalize() {
   for (auto& kv : loaders_)
     if (!kv.second.loaded) { err_ = "missing weight: " + kv.first; return MVB_ERR_STATE; }
@@ -765,6 +876,7 @@ bool Engine::run(const mvb_unet_args& a, Arena& ar, cudaStream_t s) {
   const int B = a.B, T = a.T, NF = f.NF;
   if (a.H % (1 << (nb - 1)) || a.W % (1 << (nb - 1))) { err_ = "H and W must be divisible by 2^(num_blocks-1)"; return false; }
   if (T > 32) { err_ = "at most 32 frames per window (temporal attention kernel)"; return false; }
+  if (B < 1 || B > 64 || a.n_vis_cond > 64) { err_ = "batch (incl. CFG) must be in 1..64 and at most 64 vision-condition frames"; return false; }
   if (a.n_vis_cond < 0 || a.vis_cond_first < 0 || a.vis_cond_first + a.n_vis_cond > T) { err_ = "bad vision condition index range"; return false; }
   if (c.need_refer_emb && a.n_refer != 0) {
     int expect = 1;

@@ -116,6 +116,7 @@ class Engine {
   explicit Engine(const mvb_config& cfg, int device, int kind = 0);
   ~Engine();
   int load_weight(const char* name, const void* dev_ptr, int is_f32, const long long* shape, int ndim);
+  int load_weights(const mvb_named_tensor* tensors, int n);
   int finalize();
   long long workspace_bytes(const mvb_unet_args& a);
   int forward(const mvb_unet_args& a, void* workspace, long long workspace_bytes, cudaStream_t stream);

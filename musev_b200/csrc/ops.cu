@@ -804,13 +804,15 @@ cudaError_t temporal_attention(cudaStream_t s, const __half* qkv, int ld, int B,
   const int wpb = 4;
   const unsigned blocks = (unsigned)((nprob + wpb - 1) / wpb);
   const float sl2 = scale * 1.4426950408889634f;
+  int cur_dev = 0;
+  cudaGetDevice(&cur_dev);
 #define MVB_TAM(N)                                                                                                  \
   case N: {                                                                                                          \
     const size_t smem = (size_t)wpb * 3 * (T + 1) * (N + 8) * sizeof(__half);                                        \
-    static size_t set##N = 0;                                                                                        \
-    if (smem > set##N) {                                                                                             \
+    static size_t set##N[64] = {};   /* per device */                                                                \
+    if (smem > set##N[cur_dev & 63]) {                                                                               \
       cudaFuncSetAttribute(temporal_attention_mma_kernel<N>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem); \
-      set##N = smem;                                                                                                 \
+      set##N[cur_dev & 63] = smem;                                                                                   \
     }                                                                                                                \
     temporal_attention_mma_kernel<N><<<blocks, wpb * 32, smem, s>>>(qkv, ld, B, T, HW, heads, d, sl2, out, ldo);    \
     break;                                                                                                           \

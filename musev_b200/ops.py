@@ -113,6 +113,8 @@ def temporal_attention(qkv, B, T, HW, heads, d, dp, scale):
 
 def groupnorm(x0, gamma, beta, groups=32, frames_per_stat=1, eps=1e-5, silu=False, x1=None):
     """x0 [NF, HW, C0] fp16 (+ x1 [NF, HW, C1]); gamma/beta fp32 [C0+C1]."""
+    assert x0.dtype == torch.float16 and x0.is_contiguous() and (x1 is None or (x1.dtype == torch.float16 and x1.is_contiguous()))
+    assert gamma.dtype == torch.float32 and beta.dtype == torch.float32
     NF, HW, C0 = x0.shape
     C1 = 0 if x1 is None else x1.shape[2]
     y = torch.empty((NF, HW, C0 + C1), dtype=torch.float16, device=x0.device)
@@ -124,6 +126,7 @@ def groupnorm(x0, gamma, beta, groups=32, frames_per_stat=1, eps=1e-5, silu=Fals
 
 
 def layernorm(x, gamma, beta, eps):
+    assert x.dtype == torch.float16 and x.is_contiguous() and gamma.dtype == torch.float32 and beta.dtype == torch.float32
     M, Cc = x.shape
     y = torch.empty_like(x)
     _capi.check(_capi.lib().mvb_op_layernorm(x.data_ptr(), M, Cc, eps, gamma.data_ptr(), beta.data_ptr(), y.data_ptr(),
@@ -137,6 +140,10 @@ def fuse_cfg_ddim(eps_sum, counter, latents, guidance, alpha_t, alpha_prev, pred
     B, Cc, T = latents.shape[:3]
     HW = latents.shape[3] * latents.shape[4]
     assert eps_sum.dtype == torch.float32 and eps_sum.is_contiguous() and latents.is_contiguous()
+    assert latents.dtype in (torch.float16, torch.float32), f"latents must be fp16 or fp32, got {latents.dtype}"
+    assert counter is None or (counter.dtype == torch.float32 and counter.is_contiguous() and counter.numel() == T)
+    for t_ in (noise, eps_out, x0_out):
+        assert t_ is None or (t_.dtype == torch.float32 and t_.is_contiguous())
     if out is None:
         out = torch.empty_like(latents)
     _capi.check(_capi.lib().mvb_fuse_cfg_ddim(
@@ -149,6 +156,10 @@ def fuse_cfg_ddim(eps_sum, counter, latents, guidance, alpha_t, alpha_prev, pred
 def accumulate_window(eps_sum, eps_win, src_t0, frames_dev):
     B2, Cc, T = eps_sum.shape[:3]
     HW = eps_sum.shape[3] * eps_sum.shape[4]
+    assert eps_sum.dtype == torch.float32 and eps_sum.is_contiguous()
+    assert eps_win.dtype in (torch.float16, torch.float32) and eps_win.is_contiguous(), "eps_win: contiguous fp16 / fp32"
+    assert frames_dev.dtype == torch.int32 and frames_dev.is_contiguous()
+    assert eps_win.shape[0] == B2 and eps_win.shape[1] == Cc and src_t0 + frames_dev.numel() <= eps_win.shape[2]
     _capi.check(_capi.lib().mvb_accumulate_window(eps_sum.data_ptr(), B2, Cc, T, HW, eps_win.data_ptr(),
                                                   int(eps_win.dtype == torch.float32), eps_win.shape[2], src_t0,
                                                   frames_dev.data_ptr(), frames_dev.numel(), _stream()))

@@ -75,12 +75,24 @@ class ParallelDenoiser:
                                                          context_stride, context_overlap, 1)]
         per_rank = assign_windows([len(c) for c in contexts], self.world)
         mine = per_rank[self.rank]
+        # A closed-loop `uniform` window with context_stride >= 2 can name a frame twice (e % num_frames, context.py:46).
+        # The reference's `noise_pred[:, :, c] = noise_pred[:, :, c] + noise_pred_c; counter[:, :, c] += 1` (:2076-2077) is
+        # an indexed assignment: for a repeated index the LAST occurrence wins and the counter grows by one. The
+        # accumulate kernel adds every listed frame exactly once, so duplicates are resolved here, on the host.
         counter = torch.zeros(T, dtype=torch.float32)
+        keep_pos: List[Optional[torch.Tensor]] = []
+        uniq_frames: List[List[int]] = []
         for c in contexts:
-            for fidx in c:
+            last = {}
+            for k, fidx in enumerate(c):
+                last[fidx] = k
+            pos = sorted(last.values())
+            uniq_frames.append([c[k] for k in pos])
+            keep_pos.append(None if len(pos) == len(c) else torch.tensor(pos, dtype=torch.long, device=dev) + n_vc)
+            for fidx in last:
                 counter[fidx] += 1                                                  # :2077, static per call
         counter = counter.to(dev)
-        frame_idx_dev = [torch.tensor(c, dtype=torch.int32, device=dev) for c in contexts]
+        frame_idx_dev = [torch.tensor(c, dtype=torch.int32, device=dev) for c in uniq_frames]
         frame_idx_long = [torch.tensor(c, dtype=torch.long, device=dev) for c in contexts]
         cond2 = torch.cat([condition_latents] * 2).to(latents.dtype)                # :1921-1926
         vis_idx = torch.arange(n_vc)
@@ -104,7 +116,10 @@ class ParallelDenoiser:
                 eps = self.unet(model_in, t, prompt_embeds, sample_index=sub_idx,
                                 vision_conditon_frames_sample_index=vis_idx, sample_frame_rate=motion_speed,
                                 do_classifier_free_guidance=True, return_dict=False, **kw)[0]   # :2045-2067
-                self.ops.accumulate_window(eps_sum, eps, n_vc, frame_idx_dev[wi])        # :2068-2078
+                if keep_pos[wi] is None:
+                    self.ops.accumulate_window(eps_sum, eps, n_vc, frame_idx_dev[wi])    # :2068-2078
+                else:                                                                    # window with repeated frames
+                    self.ops.accumulate_window(eps_sum, eps.index_select(2, keep_pos[wi]).contiguous(), 0, frame_idx_dev[wi])
             if self.world > 1:
                 self._dist.all_reduce(eps_sum, op=self._dist.ReduceOp.SUM, group=self.pg)
             a_t, a_p, _ = sch.step_scalars(t, 0.0)

@@ -122,7 +122,10 @@ class DDIMScheduler:
             if variance_noise is not None and generator is not None:
                 raise ValueError("Cannot pass both generator and variance_noise. Please make sure that either `generator` or"
                                  " `variance_noise` stays `None`.")
-            if variance_noise is None:
+            # musev/schedulers/scheduling_ddim.py:273-292: the reference commented out the `if variance_noise is None`
+            # guard and ALWAYS redraws the noise from `generator`; a caller-supplied tensor is ignored. Same here, unless
+            # `self.honor_variance_noise` is set (an extension for deterministic tests; off by default).
+            if variance_noise is None or not getattr(self, "honor_variance_noise", False):
                 variance_noise = _variance_noise(model_output, generator, noise_type, w_ind_noise)
             noise = variance_noise.to(sample.device).contiguous().float().view(x5.shape)
         x0 = torch.empty(x5.shape, dtype=torch.float32, device=x.device)

@@ -53,7 +53,47 @@ class MvbUnetArgs(C.Structure):
     ]
 
 
+class MvbNamedTensor(C.Structure):
+    _fields_ = [("name", C.c_char_p), ("device_ptr", C.c_void_p), ("is_f32", C.c_int), ("ndim", C.c_int),
+                ("shape", C.c_longlong * 5)]
+
+
 _declared = False
+PACK_BATCH_BYTES = 512 << 20     # source bytes staged on the device per mvb_load_weights call
+
+
+def load_weights_batched(handle, named_tensors, device) -> None:
+    """Feeds (name, tensor) pairs to `mvb_load_weights` in batches of ~PACK_BATCH_BYTES: one host->device staging copy
+    per tensor, ONE packing kernel per batch (the per-tensor entry point costs a launch + a sync per tensor)."""
+    l = _lib()
+    batch, keep, nbytes = [], [], 0
+
+    def flush():
+        nonlocal batch, keep, nbytes
+        if not batch:
+            return
+        arr = (MvbNamedTensor * len(batch))(*batch)
+        rc = l.mvb_load_weights(handle, arr, len(batch))
+        if rc != 0:
+            raise _capi.MvbError(f"mvb_load_weights: {l.mvb_handle_error(handle).decode()}")
+        batch, keep, nbytes = [], [], 0
+
+    for name, t in named_tensors:
+        if t.dtype not in (torch.float16, torch.float32):
+            t = t.float()
+        t = t.to(device).contiguous()
+        e = MvbNamedTensor()
+        e.name, e.device_ptr, e.is_f32, e.ndim = name.encode(), t.data_ptr(), _is_f32(t), t.dim()
+        for i, v in enumerate(t.shape):
+            e.shape[i] = v
+        batch.append(e)
+        keep.append(t)
+        nbytes += t.numel() * t.element_size()
+        if nbytes >= PACK_BATCH_BYTES:
+            torch.cuda.current_stream(device).synchronize()
+            flush()
+    torch.cuda.current_stream(device).synchronize()
+    flush()
 
 
 def _lib():
@@ -66,6 +106,8 @@ def _lib():
         l.mvb_destroy.restype = None
         l.mvb_load_weight.argtypes = [C.c_void_p, C.c_char_p, C.c_void_p, C.c_int, C.POINTER(C.c_longlong), C.c_int]
         l.mvb_load_weight.restype = C.c_int
+        l.mvb_load_weights.argtypes = [C.c_void_p, C.POINTER(MvbNamedTensor), C.c_int]
+        l.mvb_load_weights.restype = C.c_int
         l.mvb_finalize.argtypes = [C.c_void_p]
         l.mvb_finalize.restype = C.c_int
         l.mvb_num_params.argtypes = [C.c_void_p]
@@ -163,28 +205,22 @@ class UNet3DConditionModel:
 
     def load_state_dict(self, state_dict: Dict[str, torch.Tensor], strict: bool = True):
         """Reference: from_pretrained_2d / load_state_dict (unet_3d_condition.py:1284-1637). Tensors are packed into
-        the kernel layouts on the device, one at a time (peak extra memory = one tensor)."""
+        the kernel layouts on the device in batches (peak extra memory = one ~512 MB staging batch)."""
         expected = unet_param_shapes(self.cfg)
         missing = [k for k in expected if k not in state_dict]
         unexpected = [k for k in state_dict if k not in expected]
         if strict and (missing or unexpected):
             raise RuntimeError(f"Error(s) in loading state_dict: missing {missing[:5]} unexpected {unexpected[:5]}")
         l = _lib()
+        todo = []
         for name, shape in expected.items():
             if name not in state_dict:
                 continue
             t = state_dict[name]
             if tuple(t.shape) != tuple(shape):
                 raise RuntimeError(f"size mismatch for {name}: {tuple(t.shape)} vs {tuple(shape)}")
-            if t.dtype not in (torch.float16, torch.float32):
-                t = t.float()
-            t = t.to(self.device).contiguous()
-            shp = (C.c_longlong * max(1, t.dim()))(*t.shape)
-            rc = l.mvb_load_weight(self._h, name.encode(), t.data_ptr(), _is_f32(t), shp, t.dim())
-            if rc != 0:
-                raise _capi.MvbError(f"mvb_load_weight({name}): {l.mvb_handle_error(self._h).decode()}")
-            torch.cuda.current_stream().synchronize()
-            del t
+            todo.append((name, t))
+        load_weights_batched(self._h, todo, self.device)
         rc = l.mvb_finalize(self._h)
         if rc != 0:
             raise _capi.MvbError(f"mvb_finalize: {l.mvb_handle_error(self._h).decode()}")

@@ -32,7 +32,13 @@ def timestep_embedding(t: torch.Tensor, dim: int) -> torch.Tensor:
 
 
 class UNet3DOracle:
-    def __init__(self, cfg, state_dict: Dict[str, torch.Tensor], device="cpu", dtype=torch.float32):
+    def __init__(self, cfg, state_dict: Dict[str, torch.Tensor], device="cpu", dtype=torch.float32, emulate=None):
+        """emulate: None (plain fp32 restatement, the pinned oracle) | "all" | "branch". The two emulation modes round
+        intermediate tensors to fp16 at the points where the CUDA engine stores them in fp16 (GEMM / norm / attention
+        outputs); "branch" leaves the residual stream (the running hidden state every layer adds into) unrounded. They
+        exist to attribute the engine's distance from the fp32 oracle to its storage precision (tools/gpu_parity_20step.py)
+        and are never used as the parity reference."""
+        self.emulate = emulate
         self.cfg = cfg
         self.sd = {k: v.to(device=device, dtype=dtype) for k, v in state_dict.items()}
         self.device = device
@@ -43,6 +49,14 @@ class UNet3DOracle:
     def _w(self, name):
         return self.sd[name]
 
+    def _q(self, x):
+        """branch tensor as the engine stores it (fp16) -- identity unless emulating"""
+        return x.half().to(x.dtype) if self.emulate else x
+
+    def _qs(self, x):
+        """residual-stream tensor: rounded only in emulate="all" """
+        return x.half().to(x.dtype) if self.emulate == "all" else x
+
     def _tap(self, name, x):
         if self.taps is not None:
             self.taps[name] = x.detach().clone()
@@ -51,10 +65,10 @@ class UNet3DOracle:
         return F.linear(x, self._w(prefix + ".weight"), self.sd.get(prefix + ".bias") if bias else None)
 
     def _gn(self, x, prefix, eps):
-        return F.group_norm(x, self.cfg.norm_num_groups, self._w(prefix + ".weight"), self._w(prefix + ".bias"), eps)
+        return self._q(F.group_norm(x, self.cfg.norm_num_groups, self._w(prefix + ".weight"), self._w(prefix + ".bias"), eps))
 
     def _ln(self, x, prefix, eps):
-        return F.layer_norm(x, (x.shape[-1],), self._w(prefix + ".weight"), self._w(prefix + ".bias"), eps)
+        return self._q(F.layer_norm(x, (x.shape[-1],), self._w(prefix + ".weight"), self._w(prefix + ".bias"), eps))
 
     def _mlp_emb(self, x, prefix):
         """TimestepEmbedding: diffusers embeddings.py:190-253 (linear_1, SiLU, linear_2)."""
@@ -71,24 +85,24 @@ class UNet3DOracle:
         (musev/models/attention_processor.py:258,292,519,724; diffusers attention_processor.py:1166-1250);
         scale = dim_head ** -0.5 (diffusers attention_processor.py:127)."""
         q, k, v = self._heads(q), self._heads(k), self._heads(v)
-        o = F.scaled_dot_product_attention(q, k, v)
+        o = F.scaled_dot_product_attention(self._q(q), self._q(k), self._q(v))
         b, h, n, d = o.shape
-        return o.permute(0, 2, 1, 3).reshape(b, n, h * d)
+        return self._q(o.permute(0, 2, 1, 3).reshape(b, n, h * d))
 
     # ------------------------------------------------------------------ blocks
     def resnet(self, x, temb, p):
         """ResnetBlock2D.forward, diffusers models/resnet.py:696-770 (time_embedding_norm='default',
         output_scale_factor=1, eps=norm_eps)."""
         cfg = self.cfg
-        h = F.silu(self._gn(x, p + ".norm1", cfg.norm_eps))
+        h = self._q(F.silu(self._gn(x, p + ".norm1", cfg.norm_eps)))
         h = F.conv2d(h, self._w(p + ".conv1.weight"), self._w(p + ".conv1.bias"), padding=1)
         t = temb if cfg.resnet_2d_skip_time_act else F.silu(temb)
-        h = h + self._linear(t, p + ".time_emb_proj")[:, :, None, None]
-        h = F.silu(self._gn(h, p + ".norm2", cfg.norm_eps))
+        h = self._q(h + self._linear(self._q(t), p + ".time_emb_proj")[:, :, None, None])
+        h = self._q(F.silu(self._gn(h, p + ".norm2", cfg.norm_eps)))
         h = F.conv2d(h, self._w(p + ".conv2.weight"), self._w(p + ".conv2.bias"), padding=1)
         if (p + ".conv_shortcut.weight") in self.sd:
-            x = F.conv2d(x, self._w(p + ".conv_shortcut.weight"), self._w(p + ".conv_shortcut.bias"))
-        return x + h
+            x = self._q(F.conv2d(self._q(x), self._w(p + ".conv_shortcut.weight"), self._w(p + ".conv_shortcut.bias")))
+        return self._qs(x + h)
 
     def temp_conv(self, x, T, p):
         """TemporalConvLayer.forward, musev/models/resnet.py:95-135: 4 x [GroupNorm over (c/g, t, h, w) -> SiLU ->
@@ -99,16 +113,18 @@ class UNet3DOracle:
         v = x.view(bt // T, T, c, hh, ww).permute(0, 2, 1, 3, 4)
         identity = v
         for i, ci in ((1, 2), (2, 3), (3, 3), (4, 3)):
-            v = F.silu(self._gn(v, f"{p}.conv{i}.0", 1e-5))
+            v = self._q(F.silu(self._gn(v, f"{p}.conv{i}.0", 1e-5)))
             v = F.conv3d(v, self._w(f"{p}.conv{i}.{ci}.weight"), self._w(f"{p}.conv{i}.{ci}.bias"), padding=(1, 0, 0))
-        v = identity + torch.abs(self._w(p + ".temporal_weight")) * v
+            if i < 4:
+                v = self._q(v)
+        v = self._qs(identity + torch.abs(self._w(p + ".temporal_weight")) * v)
         return v.permute(0, 2, 1, 3, 4).reshape(bt, c, hh, ww)
 
     def feed_forward(self, x, p):
         """FeedForward with GEGLU, diffusers models/attention.py:342-395, activations.py:89-102 (erf GELU)."""
         h = self._linear(x, p + ".ff.net.0.proj")
         val, gate = h.chunk(2, dim=-1)
-        return self._linear(val * F.gelu(gate), p + ".ff.net.2")
+        return self._linear(self._q(val * F.gelu(gate)), p + ".ff.net.2")
 
     def spatial_block(self, x, enc, T, p, vis_idx, clip_emb, ip_scale):
         """musev BasicTransformerBlock.forward (musev/models/attention.py:172-431) for a spatial layer.
@@ -119,6 +135,7 @@ class UNet3DOracle:
         The CFG recompute at attention.py:319-334 is dead code (Q3) and is not restated."""
         n = self._ln(x, p + ".norm1", 0.0)
         q = self._linear(n, p + ".attn1.to_q", bias=False)
+        enc = self._q(enc)
         kv_src = n
         if self.cfg.need_t2i_ip_adapter and vis_idx is not None and T > 1:
             bt, hw, c = n.shape
@@ -127,19 +144,19 @@ class UNet3DOracle:
             kv_src = torch.cat([nb, ip], dim=2).reshape(bt, -1, c)
         k = self._linear(kv_src, p + ".attn1.to_k", bias=False)
         v = self._linear(kv_src, p + ".attn1.to_v", bias=False)
-        x = self._linear(self._sdpa(q, k, v), p + ".attn1.to_out.0") + x
+        x = self._qs(self._linear(self._sdpa(q, k, v), p + ".attn1.to_out.0") + x)
         n = self._ln(x, p + ".norm2", 1e-5)
         q = self._linear(n, p + ".attn2.to_q", bias=False)
         k = self._linear(enc, p + ".attn2.to_k", bias=False)
         v = self._linear(enc, p + ".attn2.to_v", bias=False)
         a = self._sdpa(q, k, v)
         if (p + ".attn2.to_k_ip.weight") in self.sd and clip_emb is not None and ip_scale > 0:
-            ik = self._linear(clip_emb, p + ".attn2.to_k_ip", bias=False)
-            iv = self._linear(clip_emb, p + ".attn2.to_v_ip", bias=False)
-            a = a + ip_scale * self._sdpa(q, ik, iv)
-        x = self._linear(a, p + ".attn2.to_out.0") + x
+            ik = self._linear(self._q(clip_emb), p + ".attn2.to_k_ip", bias=False)
+            iv = self._linear(self._q(clip_emb), p + ".attn2.to_v_ip", bias=False)
+            a = self._q(a + ip_scale * self._sdpa(q, ik, iv))
+        x = self._qs(self._linear(a, p + ".attn2.to_out.0") + x)
         n = self._ln(x, p + ".norm3", 0.0)
-        return self.feed_forward(n, p) + x
+        return self._qs(self.feed_forward(n, p) + x)
 
     def temporal_block(self, x, p):
         """musev BasicTransformerBlock with double_self_attention=True (temporal_transformer.py:145-163):
@@ -147,25 +164,25 @@ class UNet3DOracle:
         n = self._ln(x, p + ".norm1", 0.0)
         a = self._sdpa(self._linear(n, p + ".attn1.to_q", False), self._linear(n, p + ".attn1.to_k", False),
                        self._linear(n, p + ".attn1.to_v", False))
-        x = self._linear(a, p + ".attn1.to_out.0") + x
+        x = self._qs(self._linear(a, p + ".attn1.to_out.0") + x)
         n = self._ln(x, p + ".norm2", 1e-5)
         a = self._sdpa(self._linear(n, p + ".attn2.to_q", False), self._linear(n, p + ".attn2.to_k", False),
                        self._linear(n, p + ".attn2.to_v", False))
-        x = self._linear(a, p + ".attn2.to_out.0") + x
+        x = self._qs(self._linear(a, p + ".attn2.to_out.0") + x)
         n = self._ln(x, p + ".norm3", 0.0)
-        return self.feed_forward(n, p) + x
+        return self._qs(self.feed_forward(n, p) + x)
 
     def spatial_transformer(self, x, enc, T, p, vis_idx, clip_emb, ip_scale):
         """musev Transformer2DModel.forward continuous path (musev/models/transformer_2d.py:257-276,313-389):
         GroupNorm(eps 1e-6) -> 1x1 conv -> tokens -> block -> 1x1 conv -> + residual."""
         bt, c, hh, ww = x.shape
         h = self._gn(x, p + ".norm", 1e-6)
-        h = F.conv2d(h, self._w(p + ".proj_in.weight"), self._w(p + ".proj_in.bias"))
+        h = self._qs(F.conv2d(h, self._w(p + ".proj_in.weight"), self._w(p + ".proj_in.bias")))
         h = h.permute(0, 2, 3, 1).reshape(bt, hh * ww, c)
         h = self.spatial_block(h, enc, T, p + ".transformer_blocks.0", vis_idx, clip_emb, ip_scale)
         h = h.reshape(bt, hh, ww, c).permute(0, 3, 1, 2)
-        h = F.conv2d(h, self._w(p + ".proj_out.weight"), self._w(p + ".proj_out.bias"))
-        return h + x
+        h = F.conv2d(self._q(h), self._w(p + ".proj_out.weight"), self._w(p + ".proj_out.bias"))
+        return self._qs(h + x)
 
     def temporal_transformer(self, x, femb, T, p):
         """TransformerTemporalModel.forward, musev/models/temporal_transformer.py:189-308: GroupNorm(eps 1e-6) over
@@ -180,12 +197,12 @@ class UNet3DOracle:
         v = self._gn(v, p + ".norm", 1e-6)
         v = v.permute(0, 3, 4, 2, 1).reshape(b * hh * ww, T, c)
         v = self._linear(v, p + ".proj_in")
-        fe = self._linear(F.silu(femb), p + ".frame_emb_proj")         # [b, T, c]
-        v = v + fe.repeat_interleave(hh * ww, dim=0)                     # align_repeat_tensor_single_dim
+        fe = self._linear(self._q(F.silu(femb)), p + ".frame_emb_proj")         # [b, T, c]
+        v = self._qs(v + fe.repeat_interleave(hh * ww, dim=0))           # align_repeat_tensor_single_dim
         v = self.temporal_block(v, p + ".transformer_blocks.0")
-        v = self._linear(v, p + ".proj_out")
+        v = self._linear(self._q(v), p + ".proj_out")
         v = v.view(b, hh, ww, T, c).permute(0, 4, 3, 1, 2)
-        v = residual + torch.abs(self._w(p + ".temporal_weight")) * v
+        v = self._qs(residual + torch.abs(self._w(p + ".temporal_weight")) * v)
         return v.permute(0, 2, 1, 3, 4).reshape(bt, c, hh, ww)
 
     def refer_fuse(self, x, ref, T, p):
@@ -196,11 +213,11 @@ class UNet3DOracle:
         tok = x.permute(0, 2, 3, 1).reshape(bt, hh * ww, c)
         r = ref.permute(0, 2, 3, 4, 1).reshape(b, -1, ref.shape[1])       # b (t2 h w) c
         r = r.repeat_interleave(T, dim=0)
-        enc = torch.cat([r, tok], dim=1)
-        a = self._sdpa(self._linear(tok, p + ".to_q", False), self._linear(enc, p + ".to_k", False),
+        enc = self._q(torch.cat([r, tok], dim=1))
+        a = self._sdpa(self._linear(self._q(tok), p + ".to_q", False), self._linear(enc, p + ".to_k", False),
                        self._linear(enc, p + ".to_v", False))
         a = self._linear(a, p + ".to_out.0")
-        return a.reshape(bt, hh, ww, c).permute(0, 3, 1, 2) + x
+        return self._qs(a.reshape(bt, hh, ww, c).permute(0, 3, 1, 2) + x)
 
     # ------------------------------------------------------------------ forward
     @torch.no_grad()
@@ -253,7 +270,7 @@ class UNet3DOracle:
             clip = vision_clip_emb.to(dev, dt).repeat_interleave(T, dim=0)
         # 4. conv_in (unet_3d_condition.py:1008-1009)
         x = sample.permute(0, 2, 1, 3, 4).reshape(B * T, -1, H, W)
-        x = F.conv2d(x, self._w("conv_in.weight"), self._w("conv_in.bias"), padding=1)
+        x = self._qs(F.conv2d(self._q(x), self._w("conv_in.weight"), self._w("conv_in.bias"), padding=1))
         self._tap("conv_in", x)
         if cfg.need_transformer_in:
             x = self.temporal_transformer(x, femb, T, "transformer_in")
@@ -291,7 +308,7 @@ class UNet3DOracle:
                 skips.append(x)
             if not final:
                 p = f"down_blocks.{i}.downsamplers.0.conv"
-                x = F.conv2d(x, self._w(p + ".weight"), self._w(p + ".bias"), stride=2, padding=1)
+                x = self._qs(F.conv2d(self._q(x), self._w(p + ".weight"), self._w(p + ".bias"), stride=2, padding=1))
                 if use_ref:
                     x = self.refer_fuse(x, block_refs[cfg.layers_per_block], T,
                                         f"down_blocks.{i}.refer_emb_attns.{cfg.layers_per_block}")
@@ -328,10 +345,10 @@ class UNet3DOracle:
                 # Upsample2D: nearest x2 then 3x3 conv (diffusers models/resnet.py:167-210)
                 x = F.interpolate(x, scale_factor=2.0, mode="nearest")
                 p = f"up_blocks.{i}.upsamplers.0.conv"
-                x = F.conv2d(x, self._w(p + ".weight"), self._w(p + ".bias"), padding=1)
+                x = self._qs(F.conv2d(self._q(x), self._w(p + ".weight"), self._w(p + ".bias"), padding=1))
                 self._tap(f"up_blocks.{i}.up", x)
         # 8. out (unet_3d_condition.py:1258-1263)
-        x = F.silu(self._gn(x, "conv_norm_out", cfg.norm_eps))
+        x = self._q(F.silu(self._gn(x, "conv_norm_out", cfg.norm_eps)))
         x = F.conv2d(x, self._w("conv_out.weight"), self._w("conv_out.bias"), padding=1)
         return x.view(B, T, -1, H, W).permute(0, 2, 1, 3, 4).contiguous()
 
