@@ -220,11 +220,27 @@ typedef struct mvb_controlnet_args {
   float scales[MVB_CONTROLNET_MAX_OUT];             /* conditioning_scale, times logspace(-1, 0) in guess mode (:826-833) */
   void* outs[MVB_CONTROLNET_MAX_OUT];               /* down residuals in order, then the mid residual: [NF, C_k, h_k, w_k] */
   int out_is_f32;
+  int out_frames;                                   /* ReferenceNet only (`num_frames`, referencenet.py:1041-1049): outputs are
+                                                       [NF / out_frames, C_k, out_frames, h_k, w_k]; 0 or 1 = (b t) c h w */
 } mvb_controlnet_args;
 int mvb_create_controlnet(const mvb_config* cfg, int device, mvb_handle** out);
 long long mvb_controlnet_workspace_bytes(mvb_handle* h, const mvb_controlnet_args* args);
 int mvb_controlnet_forward(mvb_handle* h, const mvb_controlnet_args* args, void* workspace, long long workspace_bytes,
                            void* stream);
+
+/* ------------------------------------------------------------------------------------------------------------------
+ * ReferenceNet one-shot.
+ * Reference: `ReferenceNet2D.forward` (musev/models/referencenet.py:640-1127) as `get_referencenet_emb` calls it once per
+ * pipeline call at step 0 (musev/pipelines/pipeline_controlnet.py:867-964,1883-1899): the reference-image VAE latents
+ * flattened to (b t) c h w, timestep 0, `encoder_hidden_states` = the IP-Adapter image tokens (or the prompt), returning the
+ * 12 down-block feature maps + the mid-block map as [b, C, t, h, w] (`need_block_embs=True`, `return_ndim=5`; the up blocks
+ * are dropped, referencenet.py:624-636). Same SD-1.5 encoder as the ControlNet above but built from the musev blocks
+ * (LayerNorm eps 0 / 1e-5 / 0), no condition embedding, no zero convolutions: the maps are the taps.
+ * Uses `mvb_controlnet_args` (`cond_latents` NULL, `scales` ignored, `out_frames` = num_frames). */
+int mvb_create_referencenet(const mvb_config* cfg, int device, mvb_handle** out);
+long long mvb_referencenet_workspace_bytes(mvb_handle* h, const mvb_controlnet_args* args);
+int mvb_referencenet_forward(mvb_handle* h, const mvb_controlnet_args* args, void* workspace, long long workspace_bytes,
+                             void* stream);
 
 /* ---------------------------------------------------------------------------------------------------------
  * Accounting (used by bench.py). category: 0 conv/linear GEMM, 1 spatial attention, 2 temporal attention,

@@ -7,8 +7,6 @@ scaling run inside libmusevb200.so (`mvb_controlnet_forward`, musev_b200/csrc/en
 call and passes `controlnet_cond_latents` on every step (pipeline_controlnet.py:1258), so it stays a handful of torch
 convolutions here, outside the per-step path.
 
-STATUS: written in round 1 after the GPU budget was spent -- compiled, but not yet run on hardware. The GPU tests for it
-(tests/test_gpu_controlnet.py) are opt-in (MVB_TEST_CONTROLNET=1) until they have passed on a B200.
 """
 from __future__ import annotations
 
@@ -38,6 +36,7 @@ class MvbControlnetArgs(C.Structure):
         ("scales", C.c_float * MAX_OUT),
         ("outs", C.c_void_p * MAX_OUT),
         ("out_is_f32", C.c_int),
+        ("out_frames", C.c_int),
     ]
 
 

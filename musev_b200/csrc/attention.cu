@@ -668,6 +668,276 @@ attention_split_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_con
   if (warp == 1) tmem_dealloc(tmem_base, 256u);
 }
 
+
+// ------------------------------------------------------------------------------------------------ ping-pong kernel
+// Head dims that fit one 64-column atom (dp <= 64: level 0 of the UNet, where 80 % of the attention time is). The
+// previous kernel was bound by the dependent-issue latency of its softmax: eight warps in lock step on ONE 128x128 score
+// tile, a row max exchanged through smem behind a named barrier, P staged through smem behind a proxy fence, and a
+// single P buffer that serialised softmax j+1 behind P.V j. This kernel restructures the work instead of tuning it:
+//   * one CTA per SM = 256 queries of one (frame, head) = TWO independent 128-query tiles; softmax warpgroup t (4 warps)
+//     owns tile t, ONE THREAD PER QUERY ROW (all 128 scores of the row in registers): no cross-thread max exchange, no
+//     named barrier, 128 independent exp chains per thread for the scheduler to interleave; the two warpgroups run half
+//     an iteration apart, so on every SM sub-partition one warp's waits are covered by the other's arithmetic;
+//   * P never touches shared memory: fp16 probabilities go registers -> TMEM (tcgen05.st) and P.V is a TS-form MMA
+//     (A operand read from tensor memory), which removes 16 st.shared.v4 + a proxy fence per thread per tile;
+//   * row max with 3-input FMNMX3 (half the instructions); exp2 split between SFU and a degree-3 FMA-pipe polynomial.
+//   TMEM (512 columns): S0 0..127 | S1 128..255 | P0 256..319 | P1 320..383 | O0 384..447 | O1 448..511.
+//   smem: Q0, Q1 16 KB each | K ring 4 x 16 KB | V ring 4 x 16 KB | barriers.
+//   warp 0 TMA producer, warp 1 MMA issuer (+ TMEM allocator), warps 2-5 softmax tile 0, warps 6-9 softmax tile 1.
+static constexpr int kPpStages = 4;
+
+template <bool kSumInV, int kPolyOf8>
+__global__ void __launch_bounds__(320, 1)
+attention_pp_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUtensorMap tmK0,
+                    const __grid_constant__ CUtensorMap tmV0, const __grid_constant__ CUtensorMap tmK1,
+                    const __grid_constant__ CUtensorMap tmV1, const __grid_constant__ AttnParams p) {
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  uint8_t* sQ = smem;                                   // [2] tiles
+  uint8_t* sK = sQ + 2 * kAtomBytes;                    // [kPpStages]
+  uint8_t* sV = sK + kPpStages * kAtomBytes;            // [kPpStages]
+  uint64_t* bars = reinterpret_cast<uint64_t*>(sV + kPpStages * kAtomBytes);
+  uint64_t* bar_q = bars;                               // 1
+  uint64_t* full_k = bars + 1;                          // [kPpStages]
+  uint64_t* empty_k = full_k + kPpStages;
+  uint64_t* full_v = empty_k + kPpStages;
+  uint64_t* empty_v = full_v + kPpStages;
+  uint64_t* bar_s = empty_v + kPpStages;                // [2] S_t(j) complete in TMEM
+  uint64_t* bar_sfree = bar_s + 2;                      // [2] warpgroup t holds S_t(j) in registers (4 warp arrivals)
+  uint64_t* bar_p = bar_sfree + 2;                      // [2] P_t(j) in TMEM, O_t rescaled (4 warp arrivals)
+  uint64_t* bar_pv = bar_p + 2;                         // [2] P_t(j) V(j) complete: P_t reusable, O_t stable
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bar_pv + 2);
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int q0 = blockIdx.x * 256;
+  const int h = blockIdx.y;
+  const int f = blockIdx.z;
+  const int t0 = (p.nk[0] + 127) / 128;
+  const int ntiles = t0 + (p.nseg > 1 ? (p.nk[1] + 127) / 128 : 0);
+
+  if (warp == 0 && lane == 0) {
+    tma_prefetch_desc(&tmQ); tma_prefetch_desc(&tmK0); tma_prefetch_desc(&tmV0);
+    mbar_init(bar_q, 1);
+    for (int s = 0; s < kPpStages; ++s) {
+      mbar_init(&full_k[s], 1); mbar_init(&empty_k[s], 1);
+      mbar_init(&full_v[s], 1); mbar_init(&empty_v[s], 1);
+    }
+    for (int t = 0; t < 2; ++t) {
+      mbar_init(&bar_s[t], 1); mbar_init(&bar_sfree[t], 4);
+      mbar_init(&bar_p[t], 4); mbar_init(&bar_pv[t], 1);
+    }
+    fence_barrier_init();
+  }
+  if (warp == 1) {
+    tmem_alloc(tmem_slot, 512u);
+    tmem_relinquish();
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  if (warp == 0) {
+    // ---- TMA producer
+    if (elect_one()) {
+      mbar_expect_tx(bar_q, 2u * kAtomBytes);
+      tma_load_2d(sQ, &tmQ, bar_q, h * p.dp, f * p.Nq + q0);
+      tma_load_2d(sQ + kAtomBytes, &tmQ, bar_q, h * p.dp, f * p.Nq + q0 + 128);
+    }
+    __syncwarp();
+    for (int j = 0; j < ntiles; ++j) {
+      int seg, k0, valid;
+      tile_info(p, j, &seg, &k0, &valid);
+      const long long row = (long long)(f / p.fdiv[seg]) * p.fmul[seg] + p.fadd[seg] + k0;
+      const int st = j % kPpStages;
+      const uint32_t ph = ((uint32_t)(j / kPpStages) & 1u) ^ 1u;
+      mbar_wait(&empty_k[st], ph);
+      if (elect_one()) {
+        mbar_expect_tx(&full_k[st], (uint32_t)kAtomBytes);
+        tma_load_2d(sK + st * kAtomBytes, seg ? &tmK1 : &tmK0, &full_k[st], h * p.dp, (int)row);
+      }
+      __syncwarp();
+      mbar_wait(&empty_v[st], ph);
+      if (elect_one()) {
+        mbar_expect_tx(&full_v[st], (uint32_t)kAtomBytes);
+        tma_load_2d(sV + st * kAtomBytes, seg ? &tmV1 : &tmV0, &full_v[st], h * p.dp, (int)row);
+      }
+      __syncwarp();
+    }
+  } else if (warp == 1) {
+    // ---- MMA issuer (warp-uniform loop, one elected lane issues)
+    const uint32_t idesc_s = make_idesc_f16(128, 128, 0, 0);
+    const uint32_t idesc_o = make_idesc_f16(128, p.dp, 0, 1);   // B (= V) is MN-major
+    const int ksteps = p.dp / 16;
+    mbar_wait(bar_q, 0);
+    auto issue_s = [&](int t, int j) {        // S_t(j) = Q_t K(j)^T
+      const int st = j % kPpStages;
+      if (t == 0) mbar_wait(&full_k[st], (uint32_t)(j / kPpStages) & 1u);
+      tc_fence_after();
+      const uint32_t aQ = smem_u32(sQ + t * kAtomBytes);
+      const uint32_t aK = smem_u32(sK + st * kAtomBytes);
+      if (elect_one()) {
+        for (int kk = 0; kk < ksteps; ++kk)
+          umma_f16_ss(tmem_base + (uint32_t)t * 128u, make_desc_k_sw128(aQ + (uint32_t)kk * 32u),
+                      make_desc_k_sw128(aK + (uint32_t)kk * 32u), idesc_s, kk != 0);
+        umma_commit(&bar_s[t]);
+        if (t == 1) umma_commit(&empty_k[st]);   // both tiles have read this K stage
+      }
+      __syncwarp();
+    };
+    issue_s(0, 0);
+    issue_s(1, 0);
+    for (int j = 0; j < ntiles; ++j) {
+      const int st = j % kPpStages;
+      for (int t = 0; t < 2; ++t) {
+        if (j + 1 < ntiles) {
+          mbar_wait(&bar_sfree[t], (uint32_t)j & 1u);   // S_t(j) is in registers: its TMEM tile may be overwritten
+          issue_s(t, j + 1);
+        }
+        if (t == 0) mbar_wait(&full_v[st], (uint32_t)(j / kPpStages) & 1u);
+        mbar_wait(&bar_p[t], (uint32_t)j & 1u);         // P_t(j) in TMEM, O_t rescaled
+        tc_fence_after();
+        const uint32_t aV = smem_u32(sV + st * kAtomBytes);
+        if (elect_one()) {
+#pragma unroll
+          for (int k16 = 0; k16 < 8; ++k16)
+            umma_f16_ts(tmem_base + 384u + (uint32_t)t * 64u, tmem_base + 256u + (uint32_t)t * 64u + (uint32_t)k16 * 8u,
+                        make_desc_mn_sw128(aV + (uint32_t)k16 * 2048u, kAtomBytes), idesc_o, (j | k16) != 0);
+          umma_commit(&bar_pv[t]);
+          if (t == 1) umma_commit(&empty_v[st]);
+        }
+        __syncwarp();
+      }
+    }
+  } else {
+    // ---- softmax warpgroup t: one thread per query row of tile t
+    const int t = (warp - 2) >> 2;
+    const int qd = warp & 3;                            // TMEM lane quarter this warp may access
+    const int row = qd * 32 + lane;
+    const uint32_t lane_off = (uint32_t)(qd * 32) << 16;
+    const uint32_t tS = tmem_base + (uint32_t)t * 128u + lane_off;
+    const uint32_t tP = tmem_base + 256u + (uint32_t)t * 64u + lane_off;
+    const uint32_t tO = tmem_base + 384u + (uint32_t)t * 64u + lane_off;
+    const uint32_t a_bar_s = smem_u32(&bar_s[t]), a_bar_sfree = smem_u32(&bar_sfree[t]), a_bar_p = smem_u32(&bar_p[t]),
+                   a_bar_pv = smem_u32(&bar_pv[t]);
+    float m = -INFINITY, l = 0.f;
+    const float sl2 = p.scale_log2;
+    for (int j = 0; j < ntiles; ++j) {
+      const int valid = j < t0 ? min(128, p.nk[0] - j * 128) : min(128, p.nk[1] - (j - t0) * 128);
+      mbar_wait_a(a_bar_s, (uint32_t)j & 1u);
+      tc_fence_after();
+      uint32_t v[128];
+      tmem_ld32(tS, *reinterpret_cast<uint32_t(*)[32]>(&v[0]));
+      tmem_ld32(tS + 32, *reinterpret_cast<uint32_t(*)[32]>(&v[32]));
+      tmem_ld32(tS + 64, *reinterpret_cast<uint32_t(*)[32]>(&v[64]));
+      tmem_ld32(tS + 96, *reinterpret_cast<uint32_t(*)[32]>(&v[96]));
+      tmem_ld_wait();
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive_a(a_bar_sfree);       // the tensor core may start S_t(j+1)
+      if (valid < 128) {
+#pragma unroll
+        for (int i = 0; i < 128; ++i)
+          if (i >= valid) v[i] = 0xff800000u;          // -inf
+      }
+      float mx0 = __uint_as_float(v[0]), mx1 = __uint_as_float(v[1]), mx2 = __uint_as_float(v[2]), mx3 = __uint_as_float(v[3]);
+#pragma unroll
+      for (int i = 4; i < 124; i += 8) {
+        mx0 = fmax3(mx0, __uint_as_float(v[i]), __uint_as_float(v[i + 1]));
+        mx1 = fmax3(mx1, __uint_as_float(v[i + 2]), __uint_as_float(v[i + 3]));
+        mx2 = fmax3(mx2, __uint_as_float(v[i + 4]), __uint_as_float(v[i + 5]));
+        mx3 = fmax3(mx3, __uint_as_float(v[i + 6]), __uint_as_float(v[i + 7]));
+      }
+      mx0 = fmax3(mx0, __uint_as_float(v[124]), __uint_as_float(v[125]));
+      mx1 = fmax3(mx1, __uint_as_float(v[126]), __uint_as_float(v[127]));
+      const float mx = fmaxf(fmaxf(mx0, mx1), fmaxf(mx2, mx3)) * sl2;
+      const bool need = mx > m + 8.f;                   // lazy rescale: P stays below 2^8, far inside fp16 range
+      float alpha = 1.f;
+      if (need) { alpha = fast_exp2(m - mx); m = mx; }
+      const F2 sl2x2 = f2_make(sl2, sl2), nmx2 = f2_make(-m, -m);
+      uint32_t pk[64];
+      float ls0 = 0.f, ls1 = 0.f;
+#pragma unroll
+      for (int i = 0; i < 64; ++i) {                    // column pair i; kPolyOf8 of every 8 pairs take the FMA-pipe exp2
+        float a0, a1;
+        f2_get(f2_fma(f2_make(__uint_as_float(v[2 * i]), __uint_as_float(v[2 * i + 1])), sl2x2, nmx2), a0, a1);
+        float p0, p1;
+        if (((i * kPolyOf8) & 7) < kPolyOf8) {
+          poly_exp2_pair(a0, a1, p0, p1);
+        } else {
+          p0 = fast_exp2(a0);
+          p1 = fast_exp2(a1);
+        }
+        const __half2 hp = __floats2half2_rn(p0, p1);
+        pk[i] = *reinterpret_cast<const uint32_t*>(&hp);
+        if (!kSumInV) {
+          const float2 back = __half22float2(hp);
+          ls0 += back.x; ls1 += back.y;
+        }
+      }
+      if (!kSumInV) l = l * alpha + (ls0 + ls1);
+      if (j > 0) {
+        mbar_wait_a(a_bar_pv, (uint32_t)(j - 1) & 1u);  // P_t free again and O_t(j-1) final before it is rescaled
+        tc_fence_after();
+        if (__any_sync(0xffffffffu, need)) {
+          for (int c0 = 0; c0 < p.dp; c0 += 16) {
+            uint32_t o[16];
+            tmem_ld16(tO + c0, o);
+            tmem_ld_wait();
+#pragma unroll
+            for (int e = 0; e < 16; ++e) o[e] = __float_as_uint(__uint_as_float(o[e]) * alpha);
+            tmem_st16(tO + c0, o);
+          }
+        }
+      }
+      tmem_st32(tP, *reinterpret_cast<uint32_t(*)[32]>(&pk[0]));
+      tmem_st32(tP + 32, *reinterpret_cast<uint32_t(*)[32]>(&pk[32]));
+      tmem_st_wait();
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive_a(a_bar_p);
+    }
+    // ---- epilogue: O_t row / row sum -> global
+    mbar_wait_a(a_bar_pv, (uint32_t)(ntiles - 1) & 1u);
+    tc_fence_after();
+    if (kSumInV) {
+      uint32_t o[16];
+      tmem_ld16(tO + (p.d / 16) * 16, o);
+      tmem_ld_wait();
+      l = __uint_as_float(o[p.d % 16 == 8 ? 8 : 0]);     // the ones column of V accumulated the row sum
+    }
+    const float inv = p.out_scale / l;
+    const int qrow = q0 + t * 128 + row;
+    const bool ok = qrow < p.Nq;
+    __half* orow = p.out + ((long long)f * p.Nq + qrow) * p.ldo + h * p.d;
+    for (int c0 = 0; c0 < p.dp; c0 += 16) {
+      uint32_t o[16];
+      tmem_ld16(tO + c0, o);
+      tmem_ld_wait();
+      if (ok) {
+#pragma unroll
+        for (int g = 0; g < 2; ++g) {
+          const int cc = c0 + g * 8;
+          if (cc < p.d) {
+            __align__(16) __half oh[8];
+            if (p.accumulate) *reinterpret_cast<uint4*>(oh) = *reinterpret_cast<const uint4*>(orow + cc);
+#pragma unroll
+            for (int e = 0; e < 8; ++e) {
+              float x = __uint_as_float(o[g * 8 + e]) * inv;
+              if (p.accumulate) x += __half2float(oh[e]);
+              oh[e] = __float2half_rn(x);
+            }
+            *reinterpret_cast<uint4*>(orow + cc) = *reinterpret_cast<const uint4*>(oh);
+          }
+        }
+      }
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) tmem_dealloc(tmem_base, 512u);
+}
+
 cudaError_t launch_attention(cudaStream_t stream, const AttnArgs& a, const char** err) {
   if (a.d % 8 || a.dp % 16 || a.dp < a.d || a.dp > 192 || a.nseg < 1 || a.nseg > 2 || a.heads < 1) {
     *err = "attention: head dim must be a multiple of 8, padded dim a multiple of 16 (<= 192), 1..2 KV segments";
@@ -759,6 +1029,30 @@ cudaError_t launch_attention(cudaStream_t stream, const AttnArgs& a, const char*
     cudaError_t e2 = cudaGetLastError();
     if (e2 != cudaSuccess) *err = "attention_split_kernel launch";
     return e2;
+  }
+  // ping-pong kernel (two query tiles per CTA, P in TMEM) for one-atom head dims; variant 1 / MVB_ATTN=1 forces the
+  // previous kernel for A/B runs
+  if (a.dp <= 64 && a.variant != 1 && attn_env != 1) {
+    static const KernelFn pp_kernels[2][4] = {
+        {attention_pp_kernel<false, 0>, attention_pp_kernel<false, 2>, attention_pp_kernel<false, 3>, attention_pp_kernel<false, 4>},
+        {attention_pp_kernel<true, 0>, attention_pp_kernel<true, 2>, attention_pp_kernel<true, 3>, attention_pp_kernel<true, 4>}};
+    static const int pp_poly_env = getenv("MVB_POLY") ? atoi(getenv("MVB_POLY")) : 3;
+    const int pp_idx = pp_poly_env <= 0 ? 0 : pp_poly_env == 2 ? 1 : pp_poly_env >= 4 ? 3 : 2;
+    const int smem_pp = (2 + 2 * kPpStages) * kAtomBytes + 1024 + 512;
+    static bool pp_set_dev[64] = {};
+    if (!pp_set_dev[cur_dev & 63]) {
+      cudaError_t e = cudaSuccess;
+      for (int x = 0; x < 2 && e == cudaSuccess; ++x)
+        for (int y = 0; y < 4 && e == cudaSuccess; ++y)
+          e = cudaFuncSetAttribute(reinterpret_cast<const void*>(pp_kernels[x][y]), cudaFuncAttributeMaxDynamicSharedMemorySize, smem_pp);
+      if (e != cudaSuccess) { *err = "cudaFuncSetAttribute(attention_pp_kernel)"; return e; }
+      pp_set_dev[cur_dev & 63] = true;
+    }
+    dim3 grid_pp((a.Nq + 255) / 256, a.heads, a.NF);
+    pp_kernels[p.sum_in_v ? 1 : 0][pp_idx]<<<grid_pp, 320, smem_pp, stream>>>(tq, tk0, tv0, tk1, tv1, p);
+    cudaError_t e = cudaGetLastError();
+    if (e != cudaSuccess) *err = "attention_pp_kernel launch";
+    return e;
   }
   kernels[p.sum_in_v ? 1 : 0][poly_idx]<<<grid, 320, smem, stream>>>(tq, tk0, tv0, tk1, tv1, p);
   cudaError_t e = cudaGetLastError();

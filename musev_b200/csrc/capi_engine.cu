@@ -56,6 +56,33 @@ int mvb_create_controlnet(const mvb_config* cfg, int device, mvb_handle** out) {
   return MVB_OK;
 }
 
+int mvb_create_referencenet(const mvb_config* cfg, int device, mvb_handle** out) {
+  if (!cfg || !out) return MVB_ERR_INVALID;
+  if (check_config(cfg) != MVB_OK) return MVB_ERR_INVALID;
+  int n_out = 2;
+  for (int i = 0; i < cfg->num_blocks; ++i) n_out += cfg->layers_per_block + (i == cfg->num_blocks - 1 ? 0 : 1);
+  if (n_out > MVB_CONTROLNET_MAX_OUT) return MVB_ERR_INVALID;
+  mvb::Engine* e = new (std::nothrow) mvb::Engine(*cfg, device, 2);
+  if (!e) return MVB_ERR_STATE;
+  if (e->error()[0]) { delete e; return MVB_ERR_CUDA; }
+  mvb_handle* h = new (std::nothrow) mvb_handle{e};
+  if (!h) { delete e; return MVB_ERR_STATE; }
+  *out = h;
+  return MVB_OK;
+}
+
+long long mvb_referencenet_workspace_bytes(mvb_handle* h, const mvb_controlnet_args* args) {
+  if (!h || !args || h->e->kind() != 2) return -1;
+  return h->e->controlnet_workspace_bytes(*args);
+}
+
+int mvb_referencenet_forward(mvb_handle* h, const mvb_controlnet_args* args, void* workspace, long long workspace_bytes,
+                             void* stream) {
+  if (!h || !args) return MVB_ERR_INVALID;
+  if (h->e->kind() != 2) return MVB_ERR_STATE;
+  return h->e->controlnet_forward(*args, workspace, workspace_bytes, (cudaStream_t)stream);
+}
+
 long long mvb_controlnet_workspace_bytes(mvb_handle* h, const mvb_controlnet_args* args) {
   if (!h || !args) return -1;
   return h->e->controlnet_workspace_bytes(*args);

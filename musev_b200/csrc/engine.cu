@@ -101,11 +101,13 @@ __global__ void pack_batch_kernel(const PackDesc* __restrict__ descs) {
 // ---------------------------------------------------------------------------------------------- construction
 Engine::Engine(const mvb_config& cfg, int device, int kind) : cfg_(cfg), device_(device), kind_(kind) {
   heads_ = cfg.heads;
-  if (kind_ == 1) {
+  if (kind_ == 1 || kind_ == 2) {
     // the encoder half of a plain SD-1.5 UNet: none of the musev switches apply
     cfg_.need_transformer_in = cfg_.use_anivv1_cfg = cfg_.resnet_2d_skip_time_act = cfg_.keep_vision_condtion = 0;
     cfg_.need_refer_emb = cfg_.ip_adapter_cross_attn = cfg_.need_t2i_ip_adapter = 0;
-    ln_eps13_ = 1e-5f;
+    // ControlNet uses the vanilla diffusers blocks (all three LayerNorm eps 1e-5); ReferenceNet2D is built from
+    // musev/models/unet_2d_blocks.py -> musev BasicTransformerBlock and inherits the eps = 0 quirk (Q1)
+    ln_eps13_ = kind_ == 1 ? 1e-5f : 0.f;
   }
   cudaSetDevice(device);
   cudaDeviceGetAttribute(&num_sms_, cudaDevAttrMultiProcessorCount, device);
@@ -297,7 +299,7 @@ void Engine::build_refer(const std::string& p, ReferAttn& r, int C) {
 }
 
 void Engine::build() {
-  if (kind_ == 1) build_controlnet(); else build_unet();
+  if (kind_ == 1 || kind_ == 2) build_controlnet(); else build_unet();
 }
 
 // ControlNetModel.__init__ (diffusers models/controlnet.py:181-447) minus the conditioning embedding (see header)
@@ -343,6 +345,7 @@ void Engine::build_controlnet() {
   build_spatial("mid_block.attentions.0", mid_st_, cm);
   build_resnet("mid_block.resnets.1", mid_res_[1], cm, cm);
   n_zero_convs_ = (int)tap_c.size() + 1;
+  if (kind_ == 2) return;   // ReferenceNet2D returns the taps themselves (referencenet.py:1063-1127): no zero convolutions
   for (int k = 0; k < (int)tap_c.size() && k < MVB_CONTROLNET_MAX_OUT - 1; ++k)
     reg_conv("controlnet_down_blocks." + std::to_string(k), zero_convs_[k], tap_c[k], tap_c[k], 1);
   reg_conv("controlnet_mid_block", zero_convs_[n_zero_convs_ - 1], cm, cm, 1);
@@ -1120,6 +1123,10 @@ bool Engine::run_controlnet(const mvb_controlnet_args& a, Arena& ar, cudaStream_
   if (NF < 1 || a.H < 1 || a.W < 1) { err_ = "controlnet: bad shape"; return false; }
   if (a.H % (1 << (nb - 1)) || a.W % (1 << (nb - 1))) { err_ = "H and W must be divisible by 2^(num_blocks-1)"; return false; }
   if (a.n_out != n_zero_convs_) { err_ = "controlnet: n_out must be the number of residual maps (12 + 1 for SD-1.5)"; return false; }
+  const bool refnet = kind_ == 2;
+  // output layout [out_b, C, out_t, h, w] with NF = out_b * out_t; ControlNet: (b t) c h w, i.e. out_t = 1
+  const int out_t = (refnet && a.out_frames > 0) ? a.out_frames : 1;
+  if (NF % out_t) { err_ = "referencenet: num_frames must divide the batch"; return false; }
   mvb_unet_args ua{};                     // what the shared layer functions read
   ua.B = NF; ua.T = 1; ua.H = a.H; ua.W = a.W; ua.n_text = a.n_text; ua.n_vis_cond = 0; ua.ip_adapter_scale = 0.f;
   Fwd f;
@@ -1169,13 +1176,14 @@ bool Engine::run_controlnet(const mvb_controlnet_args& a, Arena& ar, cudaStream_
   {
     const size_t mk = f.mark();
     __half* A = f.alloc_h(M, 64);
-    __half* cond = f.alloc_h(M, c0);
+    __half* cond = refnet ? nullptr : f.alloc_h(M, c0);
     if (!ar.dry && f.ok) {
       cudaError_t e = im2col_latent(s, a.sample, a.sample_is_f32, NF, c.in_channels, 1, Hc, Wc, A);
-      if (e == cudaSuccess) e = ncthw_to_tokens(s, a.cond_latents, a.cond_is_f32, NF, c0, 1, Hc * Wc, cond, c0, 1.f);
+      if (e == cudaSuccess && !refnet) e = ncthw_to_tokens(s, a.cond_latents, a.cond_is_f32, NF, c0, 1, Hc * Wc, cond, c0, 1.f);
       if (e != cudaSuccess) f.fail("controlnet inputs", e);
     }
-    Epilogue ep; ep.out = x; ep.ldc = c0; ep.res = cond; ep.ld_res = c0;
+    Epilogue ep; ep.out = x; ep.ldc = c0;
+    if (!refnet) { ep.res = cond; ep.ld_res = c0; }
     f.gemm(A, M, 64, conv_in_, ep);
     f.release(mk);
   }
@@ -1217,12 +1225,16 @@ bool Engine::run_controlnet(const mvb_controlnet_args& a, Arena& ar, cudaStream_
     const TapT& t = tp[k];
     const long long Mk = (long long)NF * t.H * t.W;
     const size_t mk = f.mark();
-    __half* o = f.alloc_h(Mk, t.C);
-    Epilogue ep; ep.out = o; ep.ldc = t.C; ep.alpha = a.scales[k];
-    f.gemm(t.p, Mk, t.C, zero_convs_[k], ep);
+    const __half* o = t.p;
+    if (!refnet) {
+      __half* oz = f.alloc_h(Mk, t.C);
+      Epilogue ep; ep.out = oz; ep.ldc = t.C; ep.alpha = a.scales[k];
+      f.gemm(t.p, Mk, t.C, zero_convs_[k], ep);
+      o = oz;
+    }
     if (!ar.dry && f.ok) {
       if (!a.outs[k]) { err_ = "controlnet: null output pointer"; return false; }
-      cudaError_t e = tokens_to_ncthw(s, o, t.C, NF, t.C, 1, t.H * t.W, a.outs[k], a.out_is_f32);
+      cudaError_t e = tokens_to_ncthw(s, o, t.C, NF / out_t, t.C, out_t, t.H * t.W, a.outs[k], a.out_is_f32);
       if (e != cudaSuccess) f.fail("controlnet output", e);
     }
     f.release(mk);
@@ -1231,7 +1243,7 @@ bool Engine::run_controlnet(const mvb_controlnet_args& a, Arena& ar, cudaStream_
 }
 
 long long Engine::controlnet_workspace_bytes(const mvb_controlnet_args& a) {
-  if (kind_ != 1) { err_ = "not a ControlNet handle"; return -1; }
+  if (kind_ != 1 && kind_ != 2) { err_ = "not a ControlNet / ReferenceNet handle"; return -1; }
   Arena ar;
   ar.dry = true;
   if (!run_controlnet(a, ar, nullptr)) return -1;
@@ -1239,9 +1251,9 @@ long long Engine::controlnet_workspace_bytes(const mvb_controlnet_args& a) {
 }
 
 int Engine::controlnet_forward(const mvb_controlnet_args& a, void* workspace, long long wbytes, cudaStream_t stream) {
-  if (kind_ != 1) { err_ = "not a ControlNet handle"; return MVB_ERR_STATE; }
+  if (kind_ != 1 && kind_ != 2) { err_ = "not a ControlNet / ReferenceNet handle"; return MVB_ERR_STATE; }
   if (!finalized_) { err_ = "mvb_finalize has not been called (or weights are missing)"; return MVB_ERR_STATE; }
-  if (!a.sample || !a.cond_latents || !a.encoder_hidden_states || !workspace) { err_ = "null pointer argument"; return MVB_ERR_INVALID; }
+  if (!a.sample || (kind_ == 1 && !a.cond_latents) || !a.encoder_hidden_states || !workspace) { err_ = "null pointer argument"; return MVB_ERR_INVALID; }
   cudaSetDevice(device_);
   Arena ar;
   ar.dry = false;

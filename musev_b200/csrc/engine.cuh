@@ -112,7 +112,8 @@ struct Arena {
 
 class Engine {
  public:
-  // kind 0: UNet3DConditionModel; kind 1: ControlNet encoder (diffusers models/controlnet.py)
+  // kind 0: UNet3DConditionModel; kind 1: ControlNet encoder (diffusers models/controlnet.py);
+  // kind 2: ReferenceNet2D encoder + mid block (musev/models/referencenet.py)
   explicit Engine(const mvb_config& cfg, int device, int kind = 0);
   ~Engine();
   int load_weight(const char* name, const void* dev_ptr, int is_f32, const long long* shape, int ndim);

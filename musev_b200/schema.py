@@ -308,3 +308,39 @@ def controlnet_param_shapes(cfg: ControlNetConfig) -> "OrderedDict[str, Tuple[in
     out["controlnet_mid_block.weight"] = (cm, cm, 1, 1)
     out["controlnet_mid_block.bias"] = (cm,)
     return out
+
+
+# ------------------------------------------------------------------------------------------------ ReferenceNet (8f-2)
+@dataclass
+class ReferenceNetConfig(ControlNetConfig):
+    """`ReferenceNet2D` as `load_referencenet_by_name("musev_referencenet")` builds it (musev/models/referencenet_loader.py
+    :109-118: need_block_embs=True, need_self_attn_block_embs=False) from an SD-1.5 `unet/config.json`: the encoder half +
+    mid block of the 2-D UNet; conv_norm_out / conv_out / up_blocks are set to None (referencenet.py:624-636)."""
+
+
+def referencenet_param_shapes(cfg: ReferenceNetConfig) -> "OrderedDict[str, Tuple[int, ...]]":
+    """name -> shape of the reference `ReferenceNet2D.state_dict()` (296 tensors at SD-1.5 size): conv_in, time_embedding,
+    down_blocks (3 x CrossAttnDownBlock2D + DownBlock2D), mid_block (musev/models/referencenet.py:213-636)."""
+    full = controlnet_param_shapes(cfg)
+    return OrderedDict((k, v) for k, v in full.items()
+                       if not (k.startswith("controlnet_cond_embedding.") or k.startswith("controlnet_down_blocks.")
+                               or k.startswith("controlnet_mid_block.")))
+
+
+@dataclass
+class ImageProjConfig:
+    """`ImageProjModel` of the IP-Adapter package (ip_adapter/ip_adapter.py, tencent-ailab/IP-Adapter@main -- a pip
+    dependency of the reference, requirements.txt:2, not vendored) with the arguments the reference passes
+    (musev/models/ip_adapter_loader.py:89-93)."""
+    cross_attention_dim: int = 768
+    clip_embeddings_dim: int = 1024
+    clip_extra_context_tokens: int = 4
+
+
+def image_proj_param_shapes(cfg: ImageProjConfig) -> "OrderedDict[str, Tuple[int, ...]]":
+    out: "OrderedDict[str, Tuple[int, ...]]" = OrderedDict()
+    out["proj.weight"] = (cfg.clip_extra_context_tokens * cfg.cross_attention_dim, cfg.clip_embeddings_dim)
+    out["proj.bias"] = (cfg.clip_extra_context_tokens * cfg.cross_attention_dim,)
+    out["norm.weight"] = (cfg.cross_attention_dim,)
+    out["norm.bias"] = (cfg.cross_attention_dim,)
+    return out

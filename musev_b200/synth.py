@@ -14,7 +14,8 @@ from typing import Dict, List, Optional, Tuple
 
 import torch
 
-from .schema import ControlNetConfig, UNetConfig, controlnet_param_shapes, refer_emb_shapes, unet_param_shapes
+from .schema import (ControlNetConfig, ImageProjConfig, ReferenceNetConfig, UNetConfig, controlnet_param_shapes,
+                     image_proj_param_shapes, refer_emb_shapes, referencenet_param_shapes, unet_param_shapes)
 
 _BRANCH_OUT = ("conv2.weight", "proj_out.weight", "to_out.0.weight", "ff.net.2.weight", "conv4.3.weight")
 # the ControlNet's zero-initialised convolutions (controlnet.py:97-99,425-444) are drawn non-zero for the same reason
@@ -30,7 +31,14 @@ def _gen(seed: int, name: str) -> torch.Generator:
 def make_state_dict(cfg, seed: int = 0, dtype: torch.dtype = torch.float32) -> "OrderedDict[str, torch.Tensor]":
     """Seeded weights for a `UNetConfig` (denoiser) or a `ControlNetConfig` (ControlNet encoder)."""
     sd: "OrderedDict[str, torch.Tensor]" = OrderedDict()
-    shapes = controlnet_param_shapes(cfg) if isinstance(cfg, ControlNetConfig) else unet_param_shapes(cfg)
+    if isinstance(cfg, ReferenceNetConfig):
+        shapes = referencenet_param_shapes(cfg)
+    elif isinstance(cfg, ControlNetConfig):
+        shapes = controlnet_param_shapes(cfg)
+    elif isinstance(cfg, ImageProjConfig):
+        shapes = image_proj_param_shapes(cfg)
+    else:
+        shapes = unet_param_shapes(cfg)
     for name, shape in shapes.items():
         g = _gen(seed, name)
         if name.endswith("temporal_weight"):
@@ -88,4 +96,19 @@ def make_controlnet_inputs(cfg: ControlNetConfig, frames: int, h: int, w: int, s
         "sample": r("cn_sample", frames, cfg.in_channels, h, w),
         "encoder_hidden_states": r("cn_text", frames, 77, cfg.cross_attention_dim),
         "controlnet_cond": torch.rand(frames, cfg.conditioning_channels, 8 * h, 8 * w, generator=_gen(seed, "cn_cond")),
+    }
+
+
+def make_referencenet_inputs(cfg: ReferenceNetConfig, batch: int, n_ref: int, h: int, w: int, n_tokens: int = 4,
+                             seed: int = 2468) -> Dict[str, object]:
+    """Synthetic call arguments of `ReferenceNet2D.forward` as `get_referencenet_emb` issues it
+    (musev/pipelines/pipeline_controlnet.py:918-929): `sample` = reference-image VAE latents (b t) c h w, timestep 0,
+    `encoder_hidden_states` = the IP-Adapter image tokens [(b t), 4 n_img, 768]."""
+    def r(name, *shape, scale=1.0):
+        return torch.randn(*shape, generator=_gen(seed, name)) * scale
+
+    return {
+        "sample": r("rn_sample", batch * n_ref, cfg.in_channels, h, w, scale=0.7),
+        "encoder_hidden_states": r("rn_tokens", batch * n_ref, n_tokens, cfg.cross_attention_dim),
+        "num_frames": n_ref,
     }

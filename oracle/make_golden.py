@@ -17,8 +17,9 @@ import torch
 
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, ROOT)
-from musev_b200.schema import ControlNetConfig, controlnet_param_shapes, preset_config, unet_param_shapes  # noqa: E402
-from musev_b200.synth import make_controlnet_inputs, make_inputs, make_state_dict  # noqa: E402
+from musev_b200.schema import (ControlNetConfig, ReferenceNetConfig, controlnet_param_shapes, preset_config,  # noqa: E402
+                               referencenet_param_shapes, unet_param_shapes)
+from musev_b200.synth import make_controlnet_inputs, make_inputs, make_referencenet_inputs, make_state_dict  # noqa: E402
 from oracle import ref_shim  # noqa: E402
 from oracle.pipeline_oracle import SD15_DDIM  # noqa: E402
 
@@ -204,13 +205,63 @@ def golden_controlnet(boc, tag, frames, h, w, t, scale, guess, wseed=3, iseed=43
     print(f"{path}: mid abs-mean {stats[-1][1]:.4f} ({time.time() - t0:.1f}s)", flush=True)
 
 
+def golden_referencenet(boc, tag, batch, n_ref, h, w, wseed=5, iseed=2468):
+    """The one-shot ReferenceNet: the unmodified `musev.models.referencenet.ReferenceNet2D`, built and
+    called the way the reference does (referencenet_loader.py:109-118; pipeline_controlnet.py:918-929: timestep 0,
+    encoder_hidden_states = IP-Adapter image tokens, return_ndim 5). 512 seeded sample positions per map."""
+    ref_shim.load()
+    from musev.models.referencenet import ReferenceNet2D
+    cfg = ReferenceNetConfig(block_out_channels=tuple(boc))
+    kw = dict(sample_size=64, in_channels=4, out_channels=4, block_out_channels=tuple(boc), layers_per_block=2,
+              cross_attention_dim=768, attention_head_dim=8, norm_num_groups=32,
+              down_block_types=("CrossAttnDownBlock2D", "CrossAttnDownBlock2D", "CrossAttnDownBlock2D", "DownBlock2D"),
+              up_block_types=("UpBlock2D", "CrossAttnUpBlock2D", "CrossAttnUpBlock2D", "CrossAttnUpBlock2D"),
+              need_self_attn_block_embs=False, need_block_embs=True)
+    t0 = time.time()
+    with torch.device("meta"):
+        m = ReferenceNet2D(**kw)
+    ref_shapes = {k: tuple(v.shape) for k, v in m.state_dict().items()}
+    mine = {k: tuple(v) for k, v in referencenet_param_shapes(cfg).items()}
+    assert ref_shapes == mine, "ReferenceNet schema mismatch vs reference state_dict"
+    sd = make_state_dict(cfg, seed=wseed)
+    m = m.to_empty(device="cpu")
+    res = m.load_state_dict(sd, strict=True)
+    assert not res.missing_keys and not res.unexpected_keys
+    m.eval()
+    inp = make_referencenet_inputs(cfg, batch=batch, n_ref=n_ref, h=h, w=w, seed=iseed)
+    with torch.no_grad():
+        down, mid, self_attn = m(inp["sample"], torch.zeros((), dtype=torch.long), inp["encoder_hidden_states"],
+                                 num_frames=n_ref, return_ndim=5)
+    assert self_attn is None
+    maps = list(down) + [mid]
+    samples, stats = [], []
+    for k, mp in enumerate(maps):
+        flat = mp.reshape(-1)
+        g = torch.Generator().manual_seed(2000 + k)
+        idx = torch.randint(0, flat.numel(), (512,), generator=g)
+        samples.append(flat[idx].clone())
+        stats.append([float(flat.mean()), float(flat.abs().mean())])
+    meta = dict(block_out_channels=list(boc), batch=batch, n_ref=n_ref, h=h, w=w, weight_seed=wseed, input_seed=iseed,
+                shapes=[list(mp.shape) for mp in maps], sample_seed_base=2000, n_samples=512,
+                source="reference musev.models.referencenet.ReferenceNet2D, CPU fp32")
+    path = os.path.join(GOLDEN, f"referencenet_{tag}.pt")
+    torch.save({"meta": meta, "samples": samples, "stats": stats}, path)
+    print(f"{path}: mid abs-mean {stats[-1][1]:.4f} ({time.time() - t0:.1f}s)", flush=True)
+
+
 if __name__ == "__main__":
     ap = argparse.ArgumentParser()
     ap.add_argument("--full", action="store_true", help="also produce the full-width (1.4 B parameter) fixtures")
-    ap.add_argument("--only", default="", help="'controlnet': regenerate only the ControlNet fixtures")
+    ap.add_argument("--only", default="", help="'controlnet' / 'referencenet': regenerate only those fixtures")
     args = ap.parse_args()
     os.makedirs(GOLDEN, exist_ok=True)
     torch.set_num_threads(os.cpu_count() or 1)
+    if args.only == "referencenet":
+        golden_referencenet(NARROW, "narrow", batch=2, n_ref=1, h=16, w=16)
+        golden_referencenet(NARROW, "narrow_t2", batch=1, n_ref=2, h=8, w=8)
+        if args.full:
+            golden_referencenet(FULL, "full", batch=2, n_ref=1, h=8, w=8)
+        sys.exit(0)
     if args.only == "controlnet":
         golden_controlnet(NARROW, "narrow", frames=3, h=16, w=16, t=601, scale=0.8, guess=False)
         golden_controlnet(NARROW, "narrow_guess", frames=2, h=8, w=8, t=301, scale=1.0, guess=True)
@@ -225,7 +276,10 @@ if __name__ == "__main__":
         del m, sd
     golden_controlnet(NARROW, "narrow", frames=3, h=16, w=16, t=601, scale=0.8, guess=False)
     golden_controlnet(NARROW, "narrow_guess", frames=2, h=8, w=8, t=301, scale=1.0, guess=True)
+    golden_referencenet(NARROW, "narrow", batch=2, n_ref=1, h=16, w=16)
+    golden_referencenet(NARROW, "narrow_t2", batch=1, n_ref=2, h=8, w=8)
     if args.full:
+        golden_referencenet(FULL, "full", batch=2, n_ref=1, h=8, w=8)
         for preset in ("musev", "musev_referencenet"):
             m, cfg, sd = golden_unet(preset, FULL, "full", batch=2, frames=2, h=8, w=8, t=601)
             del m, sd

@@ -178,3 +178,25 @@ def test_controlnet_oracle_matches_reference(tag):
     down2, mid2 = oracle(inp["sample"], m["timestep"], inp["encoder_hidden_states"], controlnet_cond_latents=lat,
                          conditioning_scale=m["conditioning_scale"], guess_mode=m["guess_mode"])
     assert torch.equal(mid, mid2) and all(torch.equal(a, b) for a, b in zip(down, down2))
+
+
+@pytest.mark.parametrize("tag", ["narrow", "narrow_t2"])
+def test_referencenet_oracle_matches_reference_golden(tag):
+    """oracle/referencenet_oracle.py against samples of the unmodified musev ReferenceNet2D (oracle/make_golden.py)."""
+    import os
+    from conftest import GOLDEN
+    from musev_b200.schema import ReferenceNetConfig
+    from musev_b200.synth import make_referencenet_inputs, make_state_dict
+    from oracle.referencenet_oracle import ReferenceNetOracle
+    g = torch.load(os.path.join(GOLDEN, f"referencenet_{tag}.pt"))
+    m = g["meta"]
+    cfg = ReferenceNetConfig(block_out_channels=tuple(m["block_out_channels"]))
+    o = ReferenceNetOracle(cfg, make_state_dict(cfg, seed=m["weight_seed"]))
+    inp = make_referencenet_inputs(cfg, batch=m["batch"], n_ref=m["n_ref"], h=m["h"], w=m["w"], seed=m["input_seed"])
+    down, mid = o(inp["sample"], 0, inp["encoder_hidden_states"], num_frames=m["n_ref"], return_ndim=5)
+    maps = list(down) + [mid]
+    assert [list(x.shape) for x in maps] == m["shapes"]
+    for k, mp in enumerate(maps):
+        flat = mp.reshape(-1)
+        idx = torch.randint(0, flat.numel(), (m["n_samples"],), generator=torch.Generator().manual_seed(m["sample_seed_base"] + k))
+        assert (flat[idx] - g["samples"][k]).abs().max().item() < 2e-5 * max(1.0, g["samples"][k].abs().max().item()), k
