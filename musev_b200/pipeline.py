@@ -56,7 +56,7 @@ class ParallelDenoiser:
         motion_speed: float = 8.0,
         eta: float = 0.0,
         unet_kwargs: Optional[dict] = None,    # down_block_refer_embs / mid_block_refer_emb / vision_clip_emb / ip_adapter_scale
-        controlnet_fn: Optional[Callable] = None,  # (window frame list, latent_model_input, t) -> (down_res, mid_res)
+        controlnet_fn: Optional[Callable] = None,  # (window frame list, latent_model_input, t, step index) -> (down_res, mid_res); see make_controlnet_fn
         callback: Optional[Callable] = None,
         guidance_scale_lst: Optional[Sequence[float]] = None,
     ) -> DenoiseOutput:
@@ -110,7 +110,7 @@ class ParallelDenoiser:
                 model_in = torch.cat([cond2, torch.cat([lat_c] * 2)], dim=2)        # :1908-1946
                 kw = dict(unet_kwargs)
                 if controlnet_fn is not None:
-                    down_res, mid_res = controlnet_fn(c, model_in, t)               # :2022-2038
+                    down_res, mid_res = controlnet_fn(c, model_in, t, i)            # :2022-2038
                     kw["down_block_additional_residuals"] = down_res
                     kw["mid_block_additional_residual"] = mid_res
                 eps = self.unet(model_in, t, prompt_embeds, sample_index=sub_idx,
@@ -128,3 +128,42 @@ class ParallelDenoiser:
             if callback is not None:
                 callback(i, t, latents)
         return DenoiseOutput(latents=latents, windows=contexts, windows_per_rank=per_rank)
+
+
+
+def make_controlnet_fn(controlnet, controlnet_latents: torch.Tensor, prompt_embeds: torch.Tensor, n_vision_cond: int,
+                       controlnet_conditioning_scale: float = 1.0, guess_mode: bool = False,
+                       controlnet_keep: Optional[Sequence[float]] = None) -> Callable:
+    """The per-window-step ControlNet call of the reference loop as a `controlnet_fn` for `ParallelDenoiser`
+    (musev/pipelines/pipeline_controlnet.py:1992-2038 window slicing, :1202-1291 `get_controlnet_emb`).
+
+    controlnet_latents: [2B, C0, n_vc + T, h, w] -- the condition embedding of every frame, vision-condition frame(s) first,
+    already duplicated for CFG ([B, ...] in guess mode); computed once per call (`controlnet_cond_latents`, :1258).
+    Returns residuals shaped `(b t) c h w` with b = 2B, which is what `UNet3DConditionModel.forward` takes."""
+    vis = list(range(n_vision_cond))
+
+    def fn(c, latent_model_input, t, i=0):
+        ctx = vis + [ci + n_vision_cond for ci in c]                                       # :1997-2000
+        idx = torch.tensor(ctx, dtype=torch.long, device=controlnet_latents.device)
+        lat_c = controlnet_latents.index_select(2, idx)                                    # :2008-2010
+        b2 = latent_model_input.shape[0]
+        if guess_mode:                                                                     # :1219-1225: cond half only
+            x = latent_model_input[b2 // 2:]
+            enc = prompt_embeds[prompt_embeds.shape[0] // 2:]
+        else:
+            x, enc = latent_model_input, prompt_embeds
+        nb, ch, tc, hh, ww = x.shape
+        x2 = x.permute(0, 2, 1, 3, 4).reshape(nb * tc, ch, hh, ww)                           # b c t h w -> (b t) c h w
+        lat2 = lat_c.permute(0, 2, 1, 3, 4).reshape(nb * tc, lat_c.shape[1], hh, ww)
+        enc2 = enc.repeat_interleave(tc, dim=0)                                            # align_repeat_tensor_single_dim
+        keep = 1.0 if controlnet_keep is None else float(controlnet_keep[i])
+        down, mid = controlnet(x2, t, enc2, controlnet_cond_latents=lat2,
+                               conditioning_scale=controlnet_conditioning_scale * keep, guess_mode=guess_mode,
+                               return_dict=False)
+        if guess_mode:                                                                     # :1275-1286: zeros for uncond
+            def pad(r):
+                r5 = r.view(nb, tc, *r.shape[1:])
+                return torch.cat([torch.zeros_like(r5), r5]).view(2 * nb * tc, *r.shape[1:])
+            down, mid = [pad(d) for d in down], pad(mid)
+        return list(down), mid
+    return fn

@@ -149,9 +149,12 @@ def denoise_loop(unet: Callable, scheduler: DDIMOracle, latents: torch.Tensor, c
                  prompt_embeds: torch.Tensor, num_inference_steps: int, guidance_scale: float,
                  context_frames: int = 12, context_overlap: int = 4, context_schedule: str = "uniform_v2",
                  context_stride: int = 1, motion_speed: float = 8.0, unet_kwargs: Optional[dict] = None,
-                 return_eps: bool = False):
+                 return_eps: bool = False, controlnet: Optional[Callable] = None,
+                 controlnet_latents: Optional[torch.Tensor] = None, controlnet_conditioning_scale: float = 1.0):
     """Loop body of MusevControlNetPipeline.__call__, musev/pipelines/pipeline_controlnet.py:1846-2117, for the
-    CFG-on case (guidance_scale > 1; Q14) without ControlNet.
+    CFG-on case (guidance_scale > 1; Q14). With `controlnet` (a callable with the diffusers ControlNetModel signature) and
+    `controlnet_latents` [2B, C0, n_vc + T, h, w] the per-window ControlNet call of :1992-2038 / :1202-1291 is included
+    (guess_mode False, controlnet_keep 1).
 
     latents [B,4,T,h,w]; condition_latents [B,4,n_vc,h,w]; prompt_embeds [2B,77,768] = cat([negative, positive]).
     `unet(sample, t, encoder_hidden_states, **kw)` returns eps [2B,4,n_vc+Tc,h,w].
@@ -176,8 +179,20 @@ def denoise_loop(unet: Callable, scheduler: DDIMOracle, latents: torch.Tensor, c
             full = torch.zeros(2 * B, C, n_vc + len(c), h, w, dtype=latents.dtype)   # batch_concat_two_tensor_with_index
             full[:, :, vis_idx] = cond
             full[:, :, sub_idx] = model_in
+            kw = dict(unet_kwargs)
+            if controlnet is not None:
+                ctx = list(range(n_vc)) + [ci + n_vc for ci in c]                    # :1997-2000
+                lat_c = controlnet_latents[:, :, ctx]                                # :2008-2013
+                nb, _, tc, _, _ = full.shape
+                x2 = full.permute(0, 2, 1, 3, 4).reshape(nb * tc, C, h, w)           # :1236-1238
+                lat2 = lat_c.permute(0, 2, 1, 3, 4).reshape(nb * tc, lat_c.shape[1], h, w)
+                enc2 = prompt_embeds.repeat_interleave(tc, dim=0)                    # :1242-1246
+                down, mid = controlnet(x2, t, enc2, controlnet_cond_latents=lat2,
+                                       conditioning_scale=controlnet_conditioning_scale)   # :1253-1262
+                kw["down_block_additional_residuals"] = down
+                kw["mid_block_additional_residual"] = mid
             eps = unet(full, t, prompt_embeds, sample_index=sub_idx, vision_conditon_frames_sample_index=vis_idx,
-                       sample_frame_rate=motion_speed, **unet_kwargs)                # :2045-2067
+                       sample_frame_rate=motion_speed, **kw)                         # :2045-2067
             eps = eps[:, :, sub_idx]                                                 # :2068-2071
             noise_pred[:, :, c] = noise_pred[:, :, c] + eps                          # :2076
             counter[:, :, c] = counter[:, :, c] + 1                                  # :2077

@@ -143,3 +143,33 @@ def test_parallel_denoise_two_ranks_gloo(tmp_path, preset):
     assert all(len(r) >= 1 for r in double["per_rank"])
     # sharding changes only the summation order of the overlap accumulation
     assert (double["latents"] - single["latents"]).abs().max().item() < 1e-5
+
+
+def test_closed_loop_window_with_repeated_frames_matches_reference_semantics():
+    """`uniform` with context_stride 2 and context_frames < T < 2 context_frames wraps (e % num_frames, context.py:46) and
+    names frames twice inside one window. The reference's indexed assignment keeps the LAST occurrence and bumps the
+    counter once (pipeline_controlnet.py:2076-2077); the loop must do the same (it used to add both and count twice)."""
+    from musev_b200.pipeline import ParallelDenoiser
+    from musev_b200.scheduler import SD15_DDIM_CONFIG, DDIMScheduler
+    from oracle.pipeline_oracle import SD15_DDIM, DDIMOracle, denoise_loop
+    T, h, w = 20, 4, 4
+    ctx = [c[0] for c in prepare_global_context("uniform", 2, T, 12, 2, 4, 1)]
+    assert any(len(set(c)) < len(c) for c in ctx), "this schedule is expected to repeat frames inside a window"
+    g = torch.Generator().manual_seed(3)
+    latents = torch.randn(1, 4, T, h, w, generator=g)
+    cond = torch.randn(1, 4, 1, h, w, generator=g)
+    prompt = torch.randn(2, 77, 8, generator=g)
+
+    def fake_unet(sample, t, enc, **k):
+        # frame-position dependent, so that the two occurrences of a repeated frame give different eps
+        pos = torch.arange(sample.shape[2], dtype=sample.dtype).view(1, 1, -1, 1, 1)
+        return torch.sin(sample * 1.3 + 0.01 * float(t) + 0.37 * pos) + enc.mean() * 0.1
+
+    den = ParallelDenoiser(lambda s, t, e, return_dict=False, do_classifier_free_guidance=True, **k: (fake_unet(s, t, e),),
+                           DDIMScheduler(**SD15_DDIM_CONFIG), device_ops=OracleOpsDouble)
+    res = den(latents, cond, prompt, num_inference_steps=3, guidance_scale=2.0, context_frames=12, context_overlap=4,
+              context_schedule="uniform", context_stride=2)
+    ref = denoise_loop(fake_unet, DDIMOracle(**SD15_DDIM), latents, cond, prompt, 3, 2.0, context_frames=12, context_overlap=4,
+                       context_schedule="uniform", context_stride=2)
+    assert res.windows == ctx
+    assert (res.latents - ref).abs().max().item() < 1e-5
