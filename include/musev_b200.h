@@ -115,6 +115,19 @@ int mvb_fuse_cfg_ddim(const float* eps_sum, const float* counter, const void* la
                       float alpha_prod_t_prev, int prediction_type, float clip_range, int use_clipped_model_output,
                       float std_dev_t, const float* variance_noise, float* eps_out, float* x0_out, void* stream);
 
+/* Fused overlap mean + classifier-free guidance + an AFFINE sampler step ("other samplers ... pure
+ * elementwise epilogues like DDIM"): x_prev = c_x x + c_e eps + c_n noise, aux = a_x x + a_e eps. Covers, with
+ * host-computed scalars and no clipping / thresholding,
+ *   EulerDiscreteScheduler.step  musev/schedulers/scheduling_euler_discrete.py:47-170 (default sampler of the predictor,
+ *                                pipeline_controlnet_predictor.py:258-261): c_x 1, c_e sigma_next - sigma_hat, aux = x0;
+ *   LCMScheduler.step            musev/schedulers/scheduling_lcm.py:196-312: prev = sqrt(a_prev) denoised + sqrt(1-a_prev) z,
+ *                                aux = denoised = c_out x0 + c_skip x;
+ *   DDIMScheduler.step           eps prediction without clipping, any eta.
+ * Same tensor conventions as mvb_fuse_cfg_ddim; noise, aux_out, eps_out may be NULL. */
+int mvb_fuse_cfg_affine(const float* eps_sum, const float* counter, const void* latents_in, void* latents_out, int is_f32,
+                        int B, int C, int T, int HW, int cfg, float guidance_scale, float c_x, float c_e, float c_n,
+                        const float* noise, float a_x, float a_e, float* aux_out, float* eps_out, void* stream);
+
 /* eps_sum[:, :, frames[i]] += eps_window[:, :, src_t0 + i] (musev/pipelines/pipeline_controlnet.py:2068-2078).
  * eps_window [2B, C, Tw, HW] fp32/fp16; frames_dev: device int32[nframes]. */
 int mvb_accumulate_window(float* eps_sum, int B2, int C, int T, int HW, const void* eps_window, int is_f32, int Tw,

@@ -76,6 +76,10 @@ def _declare(l: C.CDLL) -> None:
                                     C.c_int, C.c_int, C.c_float, C.c_float, C.c_float, C.c_int, C.c_float, C.c_int,
                                     C.c_float, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]
     l.mvb_fuse_cfg_ddim.restype = C.c_int
+    l.mvb_fuse_cfg_affine.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int,
+                                      C.c_int, C.c_int, C.c_float, C.c_float, C.c_float, C.c_float, C.c_void_p, C.c_float,
+                                      C.c_float, C.c_void_p, C.c_void_p, C.c_void_p]
+    l.mvb_fuse_cfg_affine.restype = C.c_int
     l.mvb_accumulate_window.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_void_p, C.c_int, C.c_int,
                                         C.c_int, C.c_void_p, C.c_int, C.c_void_p]
     l.mvb_accumulate_window.restype = C.c_int

@@ -114,6 +114,16 @@ int mvb_fuse_cfg_ddim(const float* eps_sum, const float* counter, const void* la
   return MVB_OK;
 }
 
+int mvb_fuse_cfg_affine(const float* eps_sum, const float* counter, const void* latents_in, void* latents_out, int is_f32,
+                        int B, int C, int T, int HW, int cfg, float guidance_scale, float c_x, float c_e, float c_n,
+                        const float* noise, float a_x, float a_e, float* aux_out, float* eps_out, void* stream) {
+  if (!eps_sum || !latents_in || !latents_out) return fail("mvb_fuse_cfg_affine: null pointer", cudaSuccess);
+  cudaError_t e = fuse_cfg_affine((cudaStream_t)stream, eps_sum, counter, latents_in, latents_out, is_f32, B, C, T, HW, cfg,
+                                  guidance_scale, c_x, c_e, c_n, noise, a_x, a_e, aux_out, eps_out);
+  if (e != cudaSuccess) return fail("mvb_fuse_cfg_affine", e);
+  return MVB_OK;
+}
+
 int mvb_accumulate_window(float* eps_sum, int B2, int C, int T, int HW, const void* eps_window, int is_f32, int Tw,
                           int src_t0, const int* frames_dev, int nframes, void* stream) {
   if (!eps_sum || !eps_window || !frames_dev) return fail("mvb_accumulate_window: null pointer", cudaSuccess);

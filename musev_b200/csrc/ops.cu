@@ -876,6 +876,45 @@ cudaError_t fuse_cfg_ddim(cudaStream_t s, const float* eps_sum, const float* cou
   return cudaGetLastError();
 }
 
+// Overlap mean + CFG + an AFFINE sampler update in one pass: every eps-linear sampler step without clipping is
+//   x_prev = c_x x + c_e eps + c_n noise     (DDIM eta >= 0, Euler discrete incl. churn, LCM; coefficients from the host)
+// and an optional second affine output aux = a_x x + a_e eps (pred_original_sample / LCM's `denoised`).
+template <typename TLat>
+__global__ void fuse_cfg_affine_kernel(const float* __restrict__ eps_sum, const float* __restrict__ counter,
+                                       const TLat* __restrict__ lat_in, TLat* __restrict__ lat_out, long long n, int T, int HW,
+                                       int cfg, float g, float c_x, float c_e, float c_n, const float* __restrict__ noise,
+                                       float a_x, float a_e, float* __restrict__ aux_out, float* __restrict__ eps_out) {
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) {
+    const int t = (int)((i / HW) % T);
+    const float cnt = counter ? counter[t] : 1.f;
+    float e = eps_sum[i] / cnt;
+    if (cfg) {
+      const float tx = eps_sum[n + i] / cnt;
+      e = e + g * (tx - e);
+    }
+    const float x = (float)lat_in[i];
+    float prev = fmaf(c_x, x, c_e * e);
+    if (noise) prev = fmaf(c_n, noise[i], prev);
+    lat_out[i] = (TLat)prev;
+    if (aux_out) aux_out[i] = fmaf(a_x, x, a_e * e);
+    if (eps_out) eps_out[i] = e;
+  }
+}
+cudaError_t fuse_cfg_affine(cudaStream_t s, const float* eps_sum, const float* counter, const void* latents_in,
+                            void* latents_out, int is_f32, int B, int C, int T, int HW, int cfg, float guidance, float c_x,
+                            float c_e, float c_n, const float* noise, float a_x, float a_e, float* aux_out, float* eps_out) {
+  ProfScope prof(s, KC_OTHER);
+  const long long n = (long long)B * C * T * HW;
+  const int blocks = (int)((n + 255) / 256 < 148 * 8 ? (n + 255) / 256 : 148 * 8);
+  if (is_f32)
+    fuse_cfg_affine_kernel<float><<<blocks, 256, 0, s>>>(eps_sum, counter, (const float*)latents_in, (float*)latents_out, n, T,
+                                                         HW, cfg, guidance, c_x, c_e, c_n, noise, a_x, a_e, aux_out, eps_out);
+  else
+    fuse_cfg_affine_kernel<__half><<<blocks, 256, 0, s>>>(eps_sum, counter, (const __half*)latents_in, (__half*)latents_out, n,
+                                                          T, HW, cfg, guidance, c_x, c_e, c_n, noise, a_x, a_e, aux_out, eps_out);
+  return cudaGetLastError();
+}
+
 template <typename TIn>
 __global__ void accumulate_window_kernel(float* __restrict__ eps_sum, int B2, int C, int T, int HW,
                                          const TIn* __restrict__ win, int Tw, int src_t0, const int* __restrict__ frames,

@@ -55,6 +55,10 @@ cudaError_t fuse_cfg_ddim(cudaStream_t s, const float* eps_sum, const float* cou
                           void* latents_out, int is_f32, int B, int C, int T, int HW, int cfg, float guidance,
                           float alpha_t, float alpha_prev, int prediction_type, float clip_range, int use_clipped,
                           float std_dev, const float* noise, float* eps_out, float* x0_out);
+// overlap mean + CFG + affine sampler step x_prev = c_x x + c_e eps + c_n noise, aux = a_x x + a_e eps (Euler / LCM / DDIM)
+cudaError_t fuse_cfg_affine(cudaStream_t s, const float* eps_sum, const float* counter, const void* latents_in,
+                            void* latents_out, int is_f32, int B, int C, int T, int HW, int cfg, float guidance, float c_x,
+                            float c_e, float c_n, const float* noise, float a_x, float a_e, float* aux_out, float* eps_out);
 // eps_sum[:, :, frames[i]] += eps_window[:, :, src_t0 + i]   (pipeline_controlnet.py:2068-2078)
 cudaError_t accumulate_window(cudaStream_t s, float* eps_sum, int B2, int C, int T, int HW, const void* eps_win,
                               int is_f32, int Tw, int src_t0, const int* frames_dev, int nframes);

@@ -153,6 +153,24 @@ def fuse_cfg_ddim(eps_sum, counter, latents, guidance, alpha_t, alpha_prev, pred
     return out
 
 
+def fuse_cfg_affine(eps_sum, counter, latents, guidance, c_x, c_e, c_n=0.0, noise=None, a_x=0.0, a_e=0.0, aux_out=None,
+                    eps_out=None, cfg=True, out=None):
+    """x_prev = c_x x + c_e eps + c_n noise (eps = overlap mean + CFG of eps_sum); aux_out = a_x x + a_e eps."""
+    B, Cc, T = latents.shape[:3]
+    HW = latents.shape[3] * latents.shape[4]
+    assert eps_sum.dtype == torch.float32 and eps_sum.is_contiguous() and latents.is_contiguous()
+    assert latents.dtype in (torch.float16, torch.float32), f"latents must be fp16 or fp32, got {latents.dtype}"
+    assert counter is None or (counter.dtype == torch.float32 and counter.is_contiguous() and counter.numel() == T)
+    for t_ in (noise, aux_out, eps_out):
+        assert t_ is None or (t_.dtype == torch.float32 and t_.is_contiguous() and t_.numel() == latents.numel())
+    if out is None:
+        out = torch.empty_like(latents)
+    _capi.check(_capi.lib().mvb_fuse_cfg_affine(
+        eps_sum.data_ptr(), _ptr(counter), latents.data_ptr(), out.data_ptr(), int(latents.dtype == torch.float32),
+        B, Cc, T, HW, int(cfg), guidance, c_x, c_e, c_n, _ptr(noise), a_x, a_e, _ptr(aux_out), _ptr(eps_out), _stream()))
+    return out
+
+
 def accumulate_window(eps_sum, eps_win, src_t0, frames_dev):
     B2, Cc, T = eps_sum.shape[:3]
     HW = eps_sum.shape[3] * eps_sum.shape[4]

@@ -17,7 +17,7 @@ import torch
 
 from . import ops
 from .context import assign_windows, prepare_global_context
-from .scheduler import DDIMScheduler, _PRED
+from .scheduler import DDIMScheduler, _PRED, _variance_noise
 
 
 @dataclass
@@ -28,7 +28,9 @@ class DenoiseOutput:
 
 
 class ParallelDenoiser:
-    def __init__(self, unet, scheduler: DDIMScheduler, process_group=None, device_ops=None):
+    def __init__(self, unet, scheduler, process_group=None, device_ops=None):
+        """scheduler: musev_b200 `DDIMScheduler` (any prediction type / clipping / eta) or one of the affine samplers of
+        musev_b200.samplers (`EulerDiscreteScheduler`, the predictor's default; `LCMScheduler`)."""
         # device_ops: module providing accumulate_window / fuse_cfg_ddim; the CUDA library unless a test injects a double
         self.ops = device_ops if device_ops is not None else ops
         self.unet = unet
@@ -59,12 +61,13 @@ class ParallelDenoiser:
         controlnet_fn: Optional[Callable] = None,  # (window frame list, latent_model_input, t, step index) -> (down_res, mid_res); see make_controlnet_fn
         callback: Optional[Callable] = None,
         guidance_scale_lst: Optional[Sequence[float]] = None,
+        generator: Optional[torch.Generator] = None,   # eta > 0 / LCM / Euler churn: source of the per-step noise
+        noise_type: str = "random",                    # or "video_fusion" (pipeline_controlnet.py:1690-1696)
+        w_ind_noise: float = 0.5,
     ) -> DenoiseOutput:
         if guidance_scale <= 1.0:
             # the reference's CFG-off branch feeds the wrong vis-cond tensor (pipeline_controlnet.py:1922-1926, Q14)
             raise NotImplementedError("parallel denoise is implemented for classifier-free guidance (guidance_scale > 1)")
-        if eta != 0.0:
-            raise NotImplementedError("the fused step implements eta = 0 (the pipeline default); use scheduler.step for eta > 0")
         unet_kwargs = dict(unet_kwargs or {})
         dev = latents.device
         B, C, T, h, w = latents.shape
@@ -98,13 +101,28 @@ class ParallelDenoiser:
         vis_idx = torch.arange(n_vc)
         eps_sum = torch.zeros((2 * B, C, T, h, w), dtype=torch.float32, device=dev)
         latents = latents.contiguous()
-        pred = _PRED[sch.config.prediction_type]
-        clip = sch.config.clip_sample_range if sch.config.clip_sample else 0.0
+        is_ddim = isinstance(sch, DDIMScheduler)
+        if is_ddim:
+            pred = _PRED[sch.config.prediction_type]
+            clip = sch.config.clip_sample_range if sch.config.clip_sample else 0.0
+
+        def step_noise():
+            """Per-step noise [B,C,T,h,w] fp32, identical on every rank (drawn on rank 0, broadcast): scheduling_ddim.py
+            :266-295, scheduling_euler_discrete.py:116-127, scheduling_lcm.py:291-300."""
+            nz = _variance_noise(latents, generator, noise_type, w_ind_noise).float().contiguous()
+            if self.world > 1:
+                self._dist.broadcast(nz, src=0, group=self.pg)
+            return nz
+
         for i, t in enumerate(sch.timesteps.tolist()):
             eps_sum.zero_()                                                         # :1870-1876
             for wi in mine:                                                         # :1900 (this rank's windows)
                 c = contexts[wi]
                 lat_c = latents.index_select(2, frame_idx_long[wi])                 # :1902
+                if not is_ddim:
+                    scale = sch.model_input_scale(t)                                # scale_model_input, :1911
+                    if scale != 1.0:
+                        lat_c = lat_c * scale
                 sub_idx = torch.arange(len(c)) + n_vc                               # :1914-1920
                 # batch_concat_two_tensor_with_index: vis-cond frames first, then the window, duplicated for CFG
                 model_in = torch.cat([cond2, torch.cat([lat_c] * 2)], dim=2)        # :1908-1946
@@ -122,9 +140,18 @@ class ParallelDenoiser:
                     self.ops.accumulate_window(eps_sum, eps.index_select(2, keep_pos[wi]).contiguous(), 0, frame_idx_dev[wi])
             if self.world > 1:
                 self._dist.all_reduce(eps_sum, op=self._dist.ReduceOp.SUM, group=self.pg)
-            a_t, a_p, _ = sch.step_scalars(t, 0.0)
             g = guidance_scale_lst[i] if guidance_scale_lst is not None else guidance_scale
-            latents = self.ops.fuse_cfg_ddim(eps_sum, counter, latents, float(g), a_t, a_p, pred, clip)  # :2079,2101-2117
+            if is_ddim:
+                a_t, a_p, std = sch.step_scalars(t, eta)
+                if std > 0.0:
+                    latents = self.ops.fuse_cfg_ddim(eps_sum, counter, latents, float(g), a_t, a_p, pred, clip, std_dev=std,
+                                                     noise=step_noise())                 # eta > 0: scheduling_ddim.py:266-295
+                else:
+                    latents = self.ops.fuse_cfg_ddim(eps_sum, counter, latents, float(g), a_t, a_p, pred, clip)  # :2079,2101-2117
+            else:
+                a = sch.affine_step(t)                                              # Euler / LCM: scalars on the host
+                latents = self.ops.fuse_cfg_affine(eps_sum, counter, latents, float(g), a.c_x, a.c_e, a.c_n,
+                                                   step_noise() if a.c_n != 0.0 else None)
             if callback is not None:
                 callback(i, t, latents)
         return DenoiseOutput(latents=latents, windows=contexts, windows_per_rank=per_rank)

@@ -158,6 +158,41 @@ def golden_ddim():
     print("ddim_sd15.pt timesteps", sched.timesteps.tolist())
 
 
+def golden_samplers():
+    """The imported musev Euler / LCM schedulers (musev/schedulers/scheduling_{euler_discrete,lcm}.py) on the SD-1.5
+    scheduler config: timesteps, sigmas, init_noise_sigma and a full deterministic loop (model = sample * t / (t + 1))."""
+    ref_shim.load()
+    from musev.schedulers import EulerDiscreteScheduler, LCMScheduler
+    g = torch.Generator().manual_seed(5)
+    x0 = torch.randn(1, 4, 3, 8, 8, generator=g)
+    out = {"x": x0}
+    e = EulerDiscreteScheduler(num_train_timesteps=1000, beta_start=0.00085, beta_end=0.012, beta_schedule="scaled_linear",
+                               steps_offset=1, timestep_spacing="leading")
+    e.set_timesteps(20)
+    x = x0 * e.init_noise_sigma
+    trace = []
+    for t in e.timesteps:
+        xs = e.scale_model_input(x, t)
+        x = e.step(xs * t / (t + 1), t, x, generator=torch.Generator().manual_seed(1)).prev_sample
+        trace.append(x.clone())
+    out["euler"] = dict(timesteps=e.timesteps.clone(), sigmas=e.sigmas.clone(), init_noise_sigma=float(e.init_noise_sigma),
+                        trace=trace)
+    l = LCMScheduler(num_train_timesteps=1000, beta_start=0.00085, beta_end=0.012, beta_schedule="scaled_linear")
+    l.set_timesteps(4)
+    gen = torch.Generator().manual_seed(7)
+    x = x0.clone()
+    trace, den = [], []
+    for t in l.timesteps:
+        r = l.step(x * t / (t + 1), t, x, generator=gen)
+        x = r.prev_sample
+        trace.append(x.clone())
+        den.append(r.denoised.clone())
+    out["lcm"] = dict(timesteps=l.timesteps.clone(), trace=trace, denoised=den, noise_seed=7)
+    out["source"] = "musev.schedulers.EulerDiscreteScheduler / LCMScheduler (imported reference), SD-1.5 betas"
+    torch.save(out, os.path.join(GOLDEN, "samplers_sd15.pt"))
+    print("samplers_sd15.pt euler timesteps", e.timesteps.tolist()[:4], "... lcm", l.timesteps.tolist())
+
+
 def golden_controlnet(boc, tag, frames, h, w, t, scale, guess, wseed=3, iseed=4321):
     """The per-window-step ControlNet: the unmodified diffusers `ControlNetModel` of the reference
     tree, called the way `get_controlnet_emb` calls it (pipeline_controlnet.py:1238-1262). The 13 residual maps are
@@ -256,6 +291,9 @@ if __name__ == "__main__":
     args = ap.parse_args()
     os.makedirs(GOLDEN, exist_ok=True)
     torch.set_num_threads(os.cpu_count() or 1)
+    if args.only == "samplers":
+        golden_samplers()
+        sys.exit(0)
     if args.only == "referencenet":
         golden_referencenet(NARROW, "narrow", batch=2, n_ref=1, h=16, w=16)
         golden_referencenet(NARROW, "narrow_t2", batch=1, n_ref=2, h=8, w=8)
@@ -270,6 +308,7 @@ if __name__ == "__main__":
         sys.exit(0)
     golden_contexts()
     golden_ddim()
+    golden_samplers()
     for preset in ("musev", "musev_referencenet"):
         m, cfg, sd = golden_unet(preset, NARROW, "narrow", batch=2, frames=4, h=16, w=16, t=601)
         golden_loop(preset, NARROW, "narrow", m, cfg)

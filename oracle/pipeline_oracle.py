@@ -174,6 +174,8 @@ def denoise_loop(unet: Callable, scheduler: DDIMOracle, latents: torch.Tensor, c
             c = context[0]
             lat_c = latents[:, :, c]                                                 # :1902
             model_in = torch.cat([lat_c] * 2)                                        # :1908-1910
+            if hasattr(scheduler, "scale_model_input"):
+                model_in = scheduler.scale_model_input(model_in, t)                  # :1911 (identity for DDIM / LCM)
             sub_idx = torch.arange(len(c)) + n_vc                                    # :1914-1920
             cond = torch.cat([condition_latents] * 2)
             full = torch.zeros(2 * B, C, n_vc + len(c), h, w, dtype=latents.dtype)   # batch_concat_two_tensor_with_index
@@ -201,5 +203,5 @@ def denoise_loop(unet: Callable, scheduler: DDIMOracle, latents: torch.Tensor, c
         noise_pred = uncond + guidance_scale * (text - uncond)
         if return_eps:
             eps_trace.append(noise_pred.clone())
-        latents, _ = scheduler.step(noise_pred, t, latents, eta=0.0)                 # :2112-2117
+        latents = scheduler.step(noise_pred, t, latents)[0]                          # :2112-2117 (eta = 0)
     return (latents, eps_trace) if return_eps else latents

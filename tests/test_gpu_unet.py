@@ -4,9 +4,9 @@ reference stored in tests/golden/ (fp32 weights).
 
 Tolerance. Storage is fp16 with fp32 accumulation (the reference itself runs fp16, scripts/inference/text2video.py:590).
 One forward on eps of std ~0.6 lands at 3e-3..8e-3 max-abs from the fp32 oracle; the fp16 rounding of the WEIGHTS alone
-moves the fp32 oracle by ~2e-3..4e-3 from the fp32 reference. The bound below (2e-2 max-abs per forward) is ~3x that
-measured level; the north-star figure of 1e-3 is below what fp16 storage of O(1) activations can resolve (2^-11
-relative per rounding) and is recorded as not met in DESIGN.md.
+moves the fp32 oracle by ~2e-3..4e-3 from the fp32 reference. FWD_TOL = 1e-2 max-abs per forward is just above the largest
+measured case; every measured distance is appended to gpurun_out/parity_measured.jsonl (`_record`). The 20-step latents
+comparison on the north star's own terms is tests/test_gpu_parity20.py.
 """
 import os
 
@@ -19,7 +19,18 @@ from musev_b200.synth import make_inputs, make_state_dict
 
 pytestmark = pytest.mark.gpu
 dev = "cuda"
-FWD_TOL = 2e-2
+FWD_TOL = 1e-2
+
+
+def _record(name, value):
+    """Measured distances go to gpurun_out/parity_measured.jsonl so that the written bounds can be audited against them."""
+    import json
+    try:
+        os.makedirs("gpurun_out", exist_ok=True)
+        with open("gpurun_out/parity_measured.jsonl", "a") as fh:
+            fh.write(json.dumps({"test": name, "value": value}) + "\n")
+    except OSError:
+        pass
 
 
 def _setup(preset, boc, built_lib, io_dtype=torch.float32):
@@ -60,6 +71,8 @@ def test_forward_vs_oracle_and_reference_golden(built_lib, preset, tag, boc):
     out = model(_to(inp["sample"], dev, torch.float32), torch.tensor(m["timestep"]), _to(inp["encoder_hidden_states"], dev, torch.float32),
                 do_classifier_free_guidance=True, **{k: _to(v, dev, torch.float32) for k, v in kw.items()}).sample
     assert out.shape == ref.shape and out.dtype == torch.float32 and not torch.isnan(out).any()
+    _record(f"fwd_{preset}_{tag}_vs_oracle", (out - ref).abs().max().item())
+    _record(f"fwd_{preset}_{tag}_vs_reference_golden", (out.cpu() - g["out"]).abs().max().item())
     assert (out - ref).abs().max().item() < FWD_TOL
     assert (out.cpu() - g["out"]).abs().max().item() < FWD_TOL            # reference itself (fp32 weights)
     # every layer output, not only the final one (catches errors that later layers would wash out)
@@ -153,8 +166,9 @@ def test_parallel_denoise_loop_vs_reference_golden(built_lib, preset):
               context_frames=m["context_frames"], context_overlap=m["context_overlap"], motion_speed=8, unet_kwargs=kw)
     assert res.windows == m["contexts"]
     err = (res.latents.cpu() - g["latents"]).abs().max().item()
-    # CFG multiplies the per-forward eps error by up to (2 g - 1) = 6 and two steps accumulate
-    assert err < 0.15, err
+    _record(f"loop_{preset}_narrow_2step_vs_reference_golden", err)
+    # CFG multiplies the per-forward eps error by up to (2 g - 1) = 6 and two steps accumulate; measured 1.5e-2 .. 2.6e-2
+    assert err < 6e-2, err
     with pytest.raises(NotImplementedError):
         den(latents.to(dev), cond.to(dev), prompt.to(dev), guidance_scale=1.0)
 
@@ -217,3 +231,40 @@ def test_full_size_vs_eager_fp16_and_timing(built_lib):
         pass
     assert torch.isfinite(got).all() and err < 4e-2
     assert ms_engine < ms_eager
+
+
+def test_parallel_denoise_loop_euler_and_eta(built_lib):
+    """The loop with the predictor's default sampler (EulerDiscreteScheduler: scaled model input + affine fused step,
+    pipeline_controlnet_predictor.py:258-261) against the oracle loop around the Euler oracle; and DDIM with eta > 0 runs the
+    fused noisy step (scheduling_ddim.py:266-295) deterministically for a seeded generator."""
+    from musev_b200.pipeline import ParallelDenoiser
+    from musev_b200.samplers import EulerDiscreteScheduler
+    from musev_b200.scheduler import SD15_DDIM_CONFIG, DDIMScheduler
+    from oracle.pipeline_oracle import denoise_loop
+    from oracle.sampler_oracle import EulerOracle
+    cfg, model, oracle = _setup("musev", (64, 128, 128, 128), built_lib)
+    gen = torch.Generator().manual_seed(17)
+    T, h, w = 12, 16, 16
+    kw = dict(num_train_timesteps=1000, beta_start=0.00085, beta_end=0.012, beta_schedule="scaled_linear",
+              timestep_spacing="leading", steps_offset=1)
+    sched = EulerDiscreteScheduler(**kw)
+    latents = torch.randn(1, 4, T, h, w, generator=gen) * float(sched.init_noise_sigma)
+    cond = torch.randn(1, 4, 1, h, w, generator=gen) * 0.5
+    prompt = torch.randn(2, 77, cfg.cross_attention_dim, generator=gen)
+    out = ParallelDenoiser(model, sched)(latents.to(dev), cond.to(dev), prompt.to(dev), num_inference_steps=3, guidance_scale=3.5,
+                                         context_frames=8, context_overlap=4).latents.cpu()
+    ref = denoise_loop(lambda s, t, e, **k: oracle(s, t, e, **k).cpu(), EulerOracle(**kw), latents, cond, prompt, 3, 3.5,
+                       context_frames=8, context_overlap=4)
+    err = (out - ref).abs().max().item() / float(sched.init_noise_sigma)
+    _record("loop_euler_narrow_3step_rel", err)
+    assert err < 2e-2, err
+    # eta > 0
+    den = ParallelDenoiser(model, DDIMScheduler(**SD15_DDIM_CONFIG))
+    lat1 = latents / float(sched.init_noise_sigma)
+    a = den(lat1.to(dev), cond.to(dev), prompt.to(dev), num_inference_steps=2, guidance_scale=3.5, context_frames=8,
+            context_overlap=4, eta=0.5, generator=torch.Generator(device=dev).manual_seed(3), noise_type="video_fusion").latents
+    b = den(lat1.to(dev), cond.to(dev), prompt.to(dev), num_inference_steps=2, guidance_scale=3.5, context_frames=8,
+            context_overlap=4, eta=0.5, generator=torch.Generator(device=dev).manual_seed(3), noise_type="video_fusion").latents
+    c = den(lat1.to(dev), cond.to(dev), prompt.to(dev), num_inference_steps=2, guidance_scale=3.5, context_frames=8,
+            context_overlap=4).latents
+    assert torch.equal(a, b) and torch.isfinite(a).all() and (a - c).abs().max().item() > 1e-2

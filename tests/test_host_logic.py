@@ -173,3 +173,43 @@ def test_closed_loop_window_with_repeated_frames_matches_reference_semantics():
                        context_schedule="uniform", context_stride=2)
     assert res.windows == ctx
     assert (res.latents - ref).abs().max().item() < 1e-5
+
+
+def test_sampler_mirrors_bookkeeping_and_affine_scalars():
+    """EulerDiscreteScheduler / LCMScheduler host mirrors: timesteps, sigmas, init_noise_sigma equal the oracle's, and the
+    affine scalars reproduce the oracle's (reference-form) step on CPU tensors."""
+    import inspect
+    from musev_b200.samplers import EulerDiscreteScheduler, LCMScheduler
+    from oracle.sampler_oracle import EulerOracle, LCMOracle
+    kw = dict(num_train_timesteps=1000, beta_start=0.00085, beta_end=0.012, beta_schedule="scaled_linear",
+              timestep_spacing="leading", steps_offset=1)
+    for pred in ("epsilon", "v_prediction"):
+        s, o = EulerDiscreteScheduler(prediction_type=pred, **kw), EulerOracle(prediction_type=pred, **kw)
+        s.set_timesteps(20)
+        o.set_timesteps(20)
+        assert torch.equal(s.timesteps, o.timesteps) and torch.allclose(s.sigmas, o.sigmas)
+        assert abs(float(s.init_noise_sigma) - float(o.init_noise_sigma)) < 1e-6
+        g = torch.Generator().manual_seed(0)
+        x, e = torch.randn(2, 4, 3, 4, 4, generator=g), torch.randn(2, 4, 3, 4, 4, generator=g)
+        for t in s.timesteps[:5]:
+            assert abs(s.model_input_scale(t) - float(o.scale_model_input(torch.ones(1), t))) < 1e-6
+            a = s.affine_step(t)
+            prev, x0 = o.step(e, t, x)
+            assert (a.c_x * x + a.c_e * e - prev).abs().max().item() < 2e-5 and a.c_n == 0.0
+            assert (a.a_x * x + a.a_e * e - x0).abs().max().item() < 2e-5
+    with pytest.raises(ValueError, match="integer indices"):
+        s.step(e, 3, x)
+    assert {"generator", "noise_type", "w_ind_noise", "s_churn"} <= set(inspect.signature(s.step).parameters)
+    l, lo = LCMScheduler(), LCMOracle()
+    l.set_timesteps(4)
+    lo.set_timesteps(4)
+    assert l.timesteps.tolist() == lo.timesteps.tolist() == [999, 759, 499, 259]
+    gen = torch.Generator().manual_seed(3)
+    for i, t in enumerate(l.timesteps):
+        a = l.affine_step(t)
+        prev, den, noise = lo.step(e, t, x, gen)
+        mine = a.c_x * x + a.c_e * e + (a.c_n * noise if noise is not None else 0)
+        assert (mine - prev).abs().max().item() < 2e-5 and (a.a_x * x + a.a_e * e - den).abs().max().item() < 2e-5
+        assert (a.c_n == 0.0) == (i == 3)
+    with pytest.raises(NotImplementedError):
+        LCMScheduler(clip_sample=True)

@@ -200,3 +200,56 @@ def test_referencenet_oracle_matches_reference_golden(tag):
         flat = mp.reshape(-1)
         idx = torch.randint(0, flat.numel(), (m["n_samples"],), generator=torch.Generator().manual_seed(m["sample_seed_base"] + k))
         assert (flat[idx] - g["samples"][k]).abs().max().item() < 2e-5 * max(1.0, g["samples"][k].abs().max().item()), k
+
+
+# ------------------------------------------------------------------ other samplers
+@pytest.mark.parametrize("pred,exp_sum,exp_mean", [("epsilon", 10.0807, 0.0131), ("v_prediction", 0.0002, 2.2676e-06)])
+def test_euler_full_loop_kat(pred, exp_sum, exp_mean):
+    """diffusers/tests/schedulers/test_scheduler_euler.py:41-110 replayed on the oracle."""
+    from oracle.sampler_oracle import EulerOracle
+    s = EulerOracle(num_train_timesteps=1100, beta_start=0.0001, beta_end=0.02, beta_schedule="linear", prediction_type=pred)
+    s.set_timesteps(10)
+    x = _dummy_sample_deter() * s.init_noise_sigma
+    for t in s.timesteps:
+        x = s.scale_model_input(x, t)          # the upstream test feeds the scaled sample back into `step`
+        x, _ = s.step(x * t / (t + 1), t, x)
+    assert abs(x.abs().sum().item() - exp_sum) < 1e-2
+    assert abs(x.abs().mean().item() - exp_mean) < 1e-3
+
+
+@pytest.mark.parametrize("steps,exp_sum,exp_mean", [(1, 18.7097, 0.0244), (10, 197.7616, 0.2575)])
+def test_lcm_full_loop_kat(steps, exp_sum, exp_mean):
+    """diffusers/tests/schedulers/test_scheduler_lcm.py:209-244 replayed on the oracle (global generator seed 0)."""
+    from oracle.sampler_oracle import LCMOracle
+    s = LCMOracle()
+    s.set_timesteps(steps)
+    g = torch.manual_seed(0)
+    x = _dummy_sample_deter()
+    for t in s.timesteps:
+        x, _, _ = s.step(x * t / (t + 1), t, x, g)
+    assert abs(x.abs().sum().item() - exp_sum) < 1e-3
+    assert abs(x.abs().mean().item() - exp_mean) < 1e-3
+
+
+def test_sampler_oracles_match_imported_musev_schedulers():
+    """tests/golden/samplers_sd15.pt: loops run by the imported musev.schedulers classes (oracle/make_golden.py)."""
+    from oracle.sampler_oracle import EulerOracle, LCMOracle
+    g = torch.load(os.path.join(GOLDEN, "samplers_sd15.pt"))
+    e = EulerOracle(num_train_timesteps=1000, beta_start=0.00085, beta_end=0.012, beta_schedule="scaled_linear",
+                    timestep_spacing="leading", steps_offset=1)
+    e.set_timesteps(20)
+    assert torch.equal(e.timesteps, g["euler"]["timesteps"]) and torch.allclose(e.sigmas, g["euler"]["sigmas"], atol=1e-6)
+    assert abs(float(e.init_noise_sigma) - g["euler"]["init_noise_sigma"]) < 1e-5
+    x = g["x"] * e.init_noise_sigma
+    for i, t in enumerate(e.timesteps):
+        xs = e.scale_model_input(x, t)
+        x, _ = e.step(xs * t / (t + 1), t, x)
+        assert (x - g["euler"]["trace"][i]).abs().max().item() < 1e-4
+    l = LCMOracle()
+    l.set_timesteps(4)
+    assert l.timesteps.tolist() == g["lcm"]["timesteps"].tolist()
+    gen = torch.Generator().manual_seed(g["lcm"]["noise_seed"])
+    x = g["x"].clone()
+    for i, t in enumerate(l.timesteps):
+        x, den, _ = l.step(x * t / (t + 1), t, x, gen)
+        assert (x - g["lcm"]["trace"][i]).abs().max().item() < 1e-5 and (den - g["lcm"]["denoised"][i]).abs().max().item() < 1e-5
