@@ -64,6 +64,24 @@ __device__ __forceinline__ void poly_exp2_pair(float a0, float a1, float& p0, fl
   p1 = __int_as_float(__float_as_int(q1) + (__float_as_int(t1) << 23));
 }
 
+// Same polynomial, for arguments that carry the -112 exponent offset of the integer fp16 packing below: returns the fp32
+// BIT PATTERNS, flushed to zero when the result would be below the fp32 normal range (n + 127 <= 0 makes the integer sum
+// negative), so that a probability below 2^-14 becomes an fp16 zero / denormal instead of a clamped 2^-13.
+__device__ __forceinline__ void poly_exp2_pair_bits(float a0, float a1, uint32_t& u0, uint32_t& u1) {
+  const F2 a = f2_make(fmaxf(a0, -160.f), fmaxf(a1, -160.f));
+  const F2 t = f2_add(a, f2_make(12582912.f, 12582912.f));
+  const F2 nf = f2_add(t, f2_make(-12582912.f, -12582912.f));
+  const F2 f = f2_fma(nf, f2_make(-1.f, -1.f), a);
+  F2 q = f2_fma(f, f2_make(0.0551716648f, 0.0551716648f), f2_make(0.242611125f, 0.242611125f));
+  q = f2_fma(q, f, f2_make(0.693260968f, 0.693260968f));
+  q = f2_fma(q, f, f2_make(0.999928057f, 0.999928057f));
+  float q0, q1, t0, t1;
+  f2_get(q, q0, q1);
+  f2_get(t, t0, t1);
+  u0 = (uint32_t)max(__float_as_int(q0) + (__float_as_int(t0) << 23), 0);
+  u1 = (uint32_t)max(__float_as_int(q1) + (__float_as_int(t1) << 23), 0);
+}
+
 __device__ __forceinline__ float fast_exp2(float x) {
   float y;
   asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
@@ -854,28 +872,34 @@ attention_pp_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_consta
       const bool need = mx > m + 8.f;                   // lazy rescale: P stays below 2^8, far inside fp16 range
       float alpha = 1.f;
       if (need) { alpha = fast_exp2(m - mx); m = mx; }
-      const F2 sl2x2 = f2_make(sl2, sl2), nmx2 = f2_make(-m, -m);
+      // fp32 -> fp16 WITHOUT the conversion instruction: F2FP.F16.F32.PACK_AB issues on the quarter-rate XU pipe next to
+      // MUFU.EX2 (measured: the kernel's time tracked (MUFU + F2FP) x 8 clk per warp instruction exactly), so it cost as
+      // much as two thirds of the exponentials. Instead the exponent offset of the two formats (127 - 15 = 112) is folded
+      // into the exp2 argument -- ex2(x - 112) has fp16's biased exponent in fp32's exponent field, and ex2.approx.ftz
+      // flushes what would be an fp16 denormal -- and the fp16 bit pattern is bits [13, 29) of the result: one shift per
+      // element and one LOP3 per pair on the integer pipe. Truncation instead of round-to-nearest is a common factor
+      // (1 - 2^-12 on average) of numerator and denominator: the row sum is accumulated from the same truncated values.
+      const F2 sl2x2 = f2_make(sl2, sl2), nmx2 = f2_make(-m - 112.f, -m - 112.f);
       uint32_t pk[64];
       float ls0 = 0.f, ls1 = 0.f;
 #pragma unroll
       for (int i = 0; i < 64; ++i) {                    // column pair i; kPolyOf8 of every 8 pairs take the FMA-pipe exp2
         float a0, a1;
         f2_get(f2_fma(f2_make(__uint_as_float(v[2 * i]), __uint_as_float(v[2 * i + 1])), sl2x2, nmx2), a0, a1);
-        float p0, p1;
+        uint32_t u0, u1;
         if (((i * kPolyOf8) & 7) < kPolyOf8) {
-          poly_exp2_pair(a0, a1, p0, p1);
+          poly_exp2_pair_bits(a0, a1, u0, u1);
         } else {
-          p0 = fast_exp2(a0);
-          p1 = fast_exp2(a1);
+          u0 = __float_as_uint(fast_exp2(a0));
+          u1 = __float_as_uint(fast_exp2(a1));
         }
-        const __half2 hp = __floats2half2_rn(p0, p1);
-        pk[i] = *reinterpret_cast<const uint32_t*>(&hp);
+        pk[i] = ((u1 << 3) & 0xffff0000u) | (u0 >> 13);
         if (!kSumInV) {
-          const float2 back = __half22float2(hp);
-          ls0 += back.x; ls1 += back.y;
+          ls0 += __uint_as_float(u0 & 0xffffe000u);
+          ls1 += __uint_as_float(u1 & 0xffffe000u);
         }
       }
-      if (!kSumInV) l = l * alpha + (ls0 + ls1);
+      if (!kSumInV) l = l * alpha + (ls0 + ls1);     // in units of 2^-112
       if (j > 0) {
         mbar_wait_a(a_bar_pv, (uint32_t)(j - 1) & 1u);  // P_t free again and O_t(j-1) final before it is rescaled
         tc_fence_after();
@@ -905,6 +929,8 @@ attention_pp_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_consta
       tmem_ld16(tO + (p.d / 16) * 16, o);
       tmem_ld_wait();
       l = __uint_as_float(o[p.d % 16 == 8 ? 8 : 0]);     // the ones column of V accumulated the row sum
+    } else {
+      l *= 5.192296858534828e33f;                         // 2^112: the register row sum was kept in the exp2 offset domain
     }
     const float inv = p.out_scale / l;
     const int qrow = q0 + t * 128 + row;

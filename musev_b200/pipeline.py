@@ -64,6 +64,7 @@ class ParallelDenoiser:
         generator: Optional[torch.Generator] = None,   # eta > 0 / LCM / Euler churn: source of the per-step noise
         noise_type: str = "random",                    # or "video_fusion" (pipeline_controlnet.py:1690-1696)
         w_ind_noise: float = 0.5,
+        cfg_split: bool = False,                       # pair the ranks: each rank of a pair runs ONE half of the CFG batch
     ) -> DenoiseOutput:
         if guidance_scale <= 1.0:
             # the reference's CFG-off branch feeds the wrong vis-cond tensor (pipeline_controlnet.py:1922-1926, Q14)
@@ -76,8 +77,29 @@ class ParallelDenoiser:
         sch.set_timesteps(num_inference_steps, device="cpu")
         contexts = [c[0] for c in prepare_global_context(context_schedule, num_inference_steps, T, context_frames,
                                                          context_stride, context_overlap, 1)]
-        per_rank = assign_windows([len(c) for c in contexts], self.world)
-        mine = per_rank[self.rank]
+        # CFG split (last row): the unconditional and the text half of the CFG batch never interact inside the
+        # UNet (Q3: the only cross-half code is dead), so ranks 2p and 2p+1 can share the windows of pair p, each running a
+        # B-row forward and filling only its half of the eps accumulator. The halves are disjoint, so the SAME single
+        # all-reduce(SUM) per step that merges the windows also merges the halves -- no extra collective. This lets a video
+        # with fewer windows than GPUs (config 2: one window) use twice the GPUs, and halves the critical path when the
+        # window count is not a multiple of the GPU count (config 4: 11 windows on 8 GPUs -> 3 half-cost forwards, not 2).
+        if cfg_split:
+            if self.world % 2:
+                raise ValueError("cfg_split needs an even number of ranks")
+            if controlnet_fn is not None:
+                raise NotImplementedError("cfg_split with a ControlNet callback is not implemented")
+            per_rank = assign_windows([len(c) for c in contexts], self.world // 2)
+            mine = per_rank[self.rank // 2]
+            half = self.rank % 2
+            rows = slice(half * B, (half + 1) * B)
+            for k, v in list(unet_kwargs.items()):               # per-batch conditioning: keep this half's rows
+                if torch.is_tensor(v) and v.dim() > 0 and v.shape[0] == 2 * B:
+                    unet_kwargs[k] = v[rows].contiguous()
+                elif isinstance(v, (list, tuple)) and v and torch.is_tensor(v[0]) and v[0].shape[0] == 2 * B:
+                    unet_kwargs[k] = [x[rows].contiguous() for x in v]
+        else:
+            per_rank = assign_windows([len(c) for c in contexts], self.world)
+            mine = per_rank[self.rank]
         # A closed-loop `uniform` window with context_stride >= 2 can name a frame twice (e % num_frames, context.py:46).
         # The reference's `noise_pred[:, :, c] = noise_pred[:, :, c] + noise_pred_c; counter[:, :, c] += 1` (:2076-2077) is
         # an indexed assignment: for a repeated index the LAST occurrence wins and the counter grows by one. The
@@ -125,19 +147,23 @@ class ParallelDenoiser:
                         lat_c = lat_c * scale
                 sub_idx = torch.arange(len(c)) + n_vc                               # :1914-1920
                 # batch_concat_two_tensor_with_index: vis-cond frames first, then the window, duplicated for CFG
-                model_in = torch.cat([cond2, torch.cat([lat_c] * 2)], dim=2)        # :1908-1946
+                if cfg_split:
+                    model_in = torch.cat([cond2[:B], lat_c], dim=2)                 # this rank's half of the CFG batch
+                else:
+                    model_in = torch.cat([cond2, torch.cat([lat_c] * 2)], dim=2)    # :1908-1946
                 kw = dict(unet_kwargs)
                 if controlnet_fn is not None:
                     down_res, mid_res = controlnet_fn(c, model_in, t, i)            # :2022-2038
                     kw["down_block_additional_residuals"] = down_res
                     kw["mid_block_additional_residual"] = mid_res
-                eps = self.unet(model_in, t, prompt_embeds, sample_index=sub_idx,
+                eps = self.unet(model_in, t, prompt_embeds[rows] if cfg_split else prompt_embeds, sample_index=sub_idx,
                                 vision_conditon_frames_sample_index=vis_idx, sample_frame_rate=motion_speed,
                                 do_classifier_free_guidance=True, return_dict=False, **kw)[0]   # :2045-2067
+                acc = eps_sum[rows] if cfg_split else eps_sum                            # contiguous leading-dim slice
                 if keep_pos[wi] is None:
-                    self.ops.accumulate_window(eps_sum, eps, n_vc, frame_idx_dev[wi])    # :2068-2078
+                    self.ops.accumulate_window(acc, eps, n_vc, frame_idx_dev[wi])        # :2068-2078
                 else:                                                                    # window with repeated frames
-                    self.ops.accumulate_window(eps_sum, eps.index_select(2, keep_pos[wi]).contiguous(), 0, frame_idx_dev[wi])
+                    self.ops.accumulate_window(acc, eps.index_select(2, keep_pos[wi]).contiguous(), 0, frame_idx_dev[wi])
             if self.world > 1:
                 self._dist.all_reduce(eps_sum, op=self._dist.ReduceOp.SUM, group=self.pg)
             g = guidance_scale_lst[i] if guidance_scale_lst is not None else guidance_scale
