@@ -43,6 +43,11 @@ def parse():
     ap.add_argument("--impl", default="musev_b200", choices=["musev_b200", "reference"])
     ap.add_argument("--preset", default=PRESET)
     ap.add_argument("--skip-cpu-baseline", action="store_true")
+    ap.add_argument("--cfg-split", action="store_true",
+                    help="pair the GPUs: one window per PAIR, each GPU of a pair runs one half of the CFG batch (N=2 = config 2 itself)")
+    ap.add_argument("--controlnet", action="store_true", help="config-4 style: ControlNet encoder per window-step")
+    ap.add_argument("--cpu-frames", type=int, default=4, help="frames of the bounded cpu_baseline sample (GPU arm)")
+    ap.add_argument("--ref-frames", type=int, default=16, help="frames of one reference-arm step (16 = the config-2 window)")
     return ap.parse_args()
 
 
@@ -83,16 +88,10 @@ class ClockSampler(threading.Thread):
 _ORACLE_CACHE = {}
 
 
-def cpu_baseline(preset: str, frames: int = 1, threads: int | None = None):
-    """The oracle (CPU restatement of the reference, oracle/unet3d_oracle.py) timed on the host cores on a bounded
-    sample: ONE window-step (UNet forward, CFG batch 2) of `frames`+1 frames at 64x64, extrapolated to 20 steps.
-    torch's CPU convolutions stop scaling (and regress) far below the box's 128 hardware threads -- the first
-    measurement with all 128 was slower than 8 cores of the build container -- so at most 32 threads are used and
-    `cores` reports exactly that."""
+def _oracle_forward_seconds(preset: str, frames: int, cores: int) -> float:
     from musev_b200.schema import preset_config
     from musev_b200.synth import make_inputs, make_state_dict
     from oracle.unet3d_oracle import UNet3DOracle
-    cores = threads or min(32, os.cpu_count() or 1)
     torch.set_num_threads(cores)
     cfg = preset_config(preset)
     if preset not in _ORACLE_CACHE:
@@ -103,31 +102,74 @@ def cpu_baseline(preset: str, frames: int = 1, threads: int | None = None):
               sample_frame_rate=8)
     t0 = time.perf_counter()
     o(inp["sample"], 601, inp["encoder_hidden_states"], **kw)
-    dt = time.perf_counter() - t0
-    return {"value": frames / (dt * DDIM_STEPS), "unit": "frames/s", "cores": cores, "kind": "port",
-            "sample": f"1 oracle UNet3D forward (fp32, B=2 CFG, {frames}+1 frames, 64x64 latents, {preset}) = {dt:.1f} s; "
-                      f"x{DDIM_STEPS} DDIM steps extrapolated"}
+    return time.perf_counter() - t0
+
+
+def _frames_per_s(seconds_per_computed_frame: float) -> float:
+    """Denoised frames/s of config 2 from the CPU cost of one computed frame: a window-step computes 16 + 1 frames (the
+    vision-condition frame rides along) and 20 window-steps denoise 16 frames."""
+    return WINDOW / ((WINDOW + 1) * seconds_per_computed_frame * DDIM_STEPS)
+
+
+def cpu_baseline(preset: str, frames: int = 4, threads: int | None = None):
+    """The oracle (CPU restatement of the reference, oracle/unet3d_oracle.py) timed on the host cores on a bounded sample:
+    ONE window-step forward (CFG batch 2, 64x64 latents) with `frames`+1 frames instead of 16+1; the cost per computed
+    frame is scaled to the 17 computed frames of the real window-step and to 20 DDIM steps.
+    torch's CPU convolutions stop scaling (and regress) far below the box's 128 hardware threads -- the first measurement
+    with all 128 was slower than 8 cores of the build container -- so at most 32 threads are used and `cores` says so."""
+    cores = threads or min(32, os.cpu_count() or 1)
+    dt = _oracle_forward_seconds(preset, frames, cores)
+    return {"value": _frames_per_s(dt / (frames + 1)), "unit": "frames/s", "cores": cores, "kind": "port",
+            "seconds_per_forward": dt, "sample_frames": frames + 1,
+            "sample": f"1 oracle UNet3D window-step forward (fp32, B=2 CFG, {frames}+1 frames, 64x64 latents, {preset}) = {dt:.1f} s "
+                      f"-> {dt / (frames + 1):.2f} s per computed frame, x17 frames per window-step, x{DDIM_STEPS} DDIM steps"}
+
+
+def bench_config(preset: str, world: int, T: int, extra: dict | None = None) -> dict:
+    """`config` of the JSON line; shared by both arms so that the driver sees the same workload description."""
+    c = {"workload": f"config2 image2video 16-frame window 512x512, {DDIM_STEPS} DDIM steps, CFG, {preset} UNet3D"
+                     + ("" if world == 1 else f"; weak scaling: {T} frames = {world} windows (16, overlap 4), 1 per GPU"),
+         "preset": preset, "frames": T, "latent_hw": [LAT_H, LAT_W], "ddim_steps": DDIM_STEPS, "windows": world}
+    if extra:
+        c.update(extra)
+    return c
 
 
 def run_reference(args):
-    """`--impl reference`: the reference's CPU path (the oracle port -- a Python reference cannot travel to the GPU box)."""
+    """`--impl reference`: the reference's CPU path (the oracle port -- a Python reference cannot travel to the GPU box),
+    `--warmup W` untimed + `--steps K` timed steps. One step = one bounded window-step forward of F+1 frames (F = 1 when
+    K + W is large, up to 4) whose per-computed-frame cost is scaled to the real 16+1-frame window-step; ONE real
+    16+1-frame forward is timed after the loop and reported next to it (`full_window_step`), so the scaling can be checked."""
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
-    vals = []
-    cb = None
-    for i in range(args.warmup + args.steps):
-        cb = cpu_baseline(args.preset, frames=1)
+    cores = min(32, os.cpu_count() or 1)
+    n = args.warmup + args.steps
+    probe = _oracle_forward_seconds(args.preset, 1, cores)                   # also loads the weights / warms the allocator
+    frames = 1
+    for f in (4, 2):
+        if n * probe * (f + 1) / 2.0 <= 200.0:
+            frames = f
+            break
+    dts = []
+    for i in range(n):
+        dt = _oracle_forward_seconds(args.preset, frames, cores)
         if i >= args.warmup:
-            vals.append(cb["value"])
-    v = sum(vals) / len(vals)
-    cb["value"] = v
+            dts.append(dt)
+    per_frame = (sum(dts) / len(dts)) / (frames + 1)
+    v = _frames_per_s(per_frame)
+    full = _oracle_forward_seconds(args.preset, WINDOW, cores)               # the real config-2 window-step, once
+    cb = {"value": v, "unit": "frames/s", "cores": cores, "kind": "port", "sample_frames": frames + 1,
+          "seconds_per_forward": sum(dts) / len(dts),
+          "full_window_step": {"frames": WINDOW + 1, "seconds": full, "value_frames_per_s": WINDOW / (full * DDIM_STEPS)},
+          "sample": f"each step = 1 oracle UNet3D window-step forward (fp32, B=2 CFG, {frames}+1 frames, 64x64, {args.preset}); "
+                    f"{per_frame:.2f} s per computed frame x17 x{DDIM_STEPS}; one real 16+1-frame forward afterwards: {full:.1f} s"}
+    T = video_frames(1)
     print(json.dumps({
         "impl": "reference", "metric": METRIC, "value": v, "unit": "frames/s", "n_gpus": args.gpus, "steps": args.steps,
-        "warmup": args.warmup, "ms_per_step": 1000.0 / (v * DDIM_STEPS) if v else None, "higher_is_better": True,
+        "warmup": args.warmup, "ms_per_step": 1000.0 * (WINDOW + 1) * per_frame * DDIM_STEPS, "higher_is_better": True,
         "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-        "config": {"workload": "config2 image2video 16-frame 512x512 20 DDIM steps (sampled: one 1+1-frame window-step per step, x20 extrapolated)",
-                   "preset": args.preset},
+        "config": bench_config(args.preset, 1, T),
         "cpu_baseline": cb,
         "e2e": {"value": v, "unit": "frames/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
     }), flush=True)
@@ -174,17 +216,39 @@ def main():
     del sd
     sched = DDIMScheduler(**SD15_DDIM_CONFIG)
     den = ParallelDenoiser(unet, sched)
-    T = video_frames(world)
+    if args.cfg_split and world % 2:
+        raise SystemExit("--cfg-split needs an even number of GPUs")
+    n_windows = world // 2 if args.cfg_split else world        # one window per GPU, or per GPU pair
+    T = video_frames(n_windows)
+    cnet_fn = None
     g = torch.Generator().manual_seed(1234)
     lat_host = torch.randn(1, 4, T, LAT_H, LAT_W, generator=g).half().pin_memory()
     cond_host = (torch.randn(1, 4, 1, LAT_H, LAT_W, generator=g) * 0.18215).half().pin_memory()
     prompt_host = torch.randn(2, 77, cfg.cross_attention_dim, generator=g).half().pin_memory()
     out_host = torch.empty(1, 4, T, LAT_H, LAT_W, dtype=torch.float16).pin_memory()
     lat, cond, prompt = lat_host.to(dev), cond_host.to(dev), prompt_host.to(dev)
+    if args.controlnet:
+        # config-4 style: the ControlNet encoder runs on the engine every window-step (+9.63 TFLOP per 34-frame call)
+        from musev_b200.controlnet import ControlNetModel
+        from musev_b200.pipeline import make_controlnet_fn
+        from musev_b200.schema import ControlNetConfig
+        ccfg = ControlNetConfig()
+        cnet = ControlNetModel(ccfg, device=dev, dtype=torch.float16)
+        cnet.load_state_dict(make_state_dict(ccfg, seed=3, dtype=torch.float16))
+        cn_lat = (torch.randn(2, ccfg.block_out_channels[0], 1 + T, LAT_H, LAT_W, generator=g) * 0.3).half().to(dev)
+        cnet_fn = make_controlnet_fn(cnet, cn_lat, prompt, 1)
 
-    def one_step(latents, cond_l, prompt_e):
+    def one_step(latents, cond_l, prompt_e, single_window=False):
+        if single_window:                       # the N = 1 workload on this rank alone (no collective): step-time reference
+            return single(latents[:, :, :WINDOW].contiguous(), cond_l, prompt_e, num_inference_steps=DDIM_STEPS,
+                          guidance_scale=GUIDANCE, context_frames=WINDOW, context_overlap=OVERLAP,
+                          context_schedule="uniform_v2", motion_speed=8.0).latents
         return den(latents, cond_l, prompt_e, num_inference_steps=DDIM_STEPS, guidance_scale=GUIDANCE,
-                   context_frames=WINDOW, context_overlap=OVERLAP, context_schedule="uniform_v2", motion_speed=8.0).latents
+                   context_frames=WINDOW, context_overlap=OVERLAP, context_schedule="uniform_v2", motion_speed=8.0,
+                   controlnet_fn=cnet_fn, cfg_split=args.cfg_split).latents
+
+    single = ParallelDenoiser(unet, sched)
+    single._dist, single.rank, single.world = None, 0, 1      # local: never enters a collective
 
     def barrier():
         if world > 1:
@@ -230,6 +294,55 @@ def main():
     h2d = lat_host.numel() * 2 + cond_host.numel() * 2 + prompt_host.numel() * 2
     d2h = out_host.numel() * 2
 
+    # ---- step-time reference for the scaling record: the N = 1 workload (one 16-frame window, CFG batch 2) on this GPU
+    ms_single = None
+    if world > 1:
+        barrier()
+        one_step(lat, cond, prompt, single_window=True)
+        torch.cuda.synchronize()
+        s0, s1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        s0.record()
+        one_step(lat, cond, prompt, single_window=True)
+        s1.record()
+        torch.cuda.synchronize()
+        t_single = torch.tensor([s0.elapsed_time(s1)], device=dev)
+        dist.all_reduce(t_single, op=dist.ReduceOp.MAX)
+        ms_single = float(t_single.item())
+    # ---- one UNet forward of each released preset at the config-2 shape (N = 1 only; CUDA events, 3 forwards)
+    forward_ms = {}
+    if world == 1:
+        from musev_b200.synth import make_inputs
+
+        def time_forward(model, mcfg):
+            inp = make_inputs(mcfg, batch=2, frames=WINDOW, h=LAT_H, w=LAT_W, n_vis_cond=1)
+            kw = dict(sample_index=inp["sample_index"], vision_conditon_frames_sample_index=inp["vision_conditon_frames_sample_index"],
+                      sample_frame_rate=8)
+            for k in ("down_block_refer_embs", "mid_block_refer_emb", "vision_clip_emb"):
+                if k in inp:
+                    kw[k] = [x.half().to(dev) for x in inp[k]] if isinstance(inp[k], list) else inp[k].half().to(dev)
+            x, enc = inp["sample"].half().to(dev), inp["encoder_hidden_states"].half().to(dev)
+            for _ in range(2):
+                model(x, 601, enc, **kw)
+            torch.cuda.synchronize()
+            f0, f1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            f0.record()
+            for _ in range(3):
+                model(x, 601, enc, **kw)
+            f1.record()
+            torch.cuda.synchronize()
+            return f0.elapsed_time(f1) / 3
+        forward_ms[args.preset] = time_forward(unet, cfg)
+        other = "musev_referencenet" if args.preset == "musev" else "musev"
+        try:
+            ocfg = preset_config(other)
+            om = UNet3DConditionModel(ocfg, device=dev, dtype=torch.float16)
+            om.load_state_dict(make_state_dict(ocfg, seed=0, dtype=torch.float16))
+            forward_ms[other] = time_forward(om, ocfg)
+            del om
+            torch.cuda.empty_cache()
+        except Exception as e:   # never fail the headline on the side measurement
+            forward_ms[other] = f"error: {e}"
+
     # ---- roofline of the dominant kernel (conv/linear tcgen05 GEMM): CUDA events around every launch of one more
     # denoise step on the launching stream (separate pass so the event records do not perturb the timed regions)
     roof = None
@@ -243,6 +356,8 @@ def main():
     if rank == 0:
         fl = unet_forward_flops(cfg, 2, WINDOW + 1, LAT_H, LAT_W)
         n_fwd = DDIM_STEPS          # one window per rank -> one UNet forward per DDIM step
+        if args.cfg_split:
+            fl = unet_forward_flops(cfg, 1, WINDOW + 1, LAT_H, LAT_W)      # each rank runs one half of the CFG batch
         gemm_ms, gemm_n = prof["gemm"]["ms"], prof["gemm"]["launches"]
         peaks = {}
         try:
@@ -279,16 +394,28 @@ def main():
             except Exception as e:  # reported baseline only; never fail the GPU number on it
                 cb = {"error": str(e)}
         fl_total = unet_forward_flops(cfg, 2, WINDOW + 1, LAT_H, LAT_W)["total"]
+        extra = {"parallelism": (f"windows sharded over {world} GPU(s), 1 NCCL all-reduce/step" if not args.cfg_split else
+                                 f"CFG split: {n_windows} window(s) over {world} GPUs, each GPU of a pair runs one half of the CFG batch, 1 NCCL all-reduce/step"),
+                 "l2_policy": "per-forward activation working set (~4 GB) >> 126 MB L2; no explicit flush",
+                 "achieved_tflops_whole_step": fl_total * DDIM_STEPS * args.steps * n_windows / (ms_total * 1e-3) / 1e12,
+                 # what bounds the weak-scaling curve: each added window brings 12 new frames for 17 computed ones
+                 "ideal_efficiency": T / (WINDOW * world),
+                 "step_time_efficiency": (ms_single / (ms_total / args.steps)) if ms_single else 1.0,
+                 "single_window_ms_per_step": ms_single}
+        if forward_ms:
+            extra["unet_forward_ms"] = forward_ms
+        if args.controlnet:
+            extra["controlnet"] = "SD-1.5 ControlNet encoder on the engine every window-step (config-4 style)"
+        conf = bench_config(args.preset, n_windows, T, extra)
+        if args.cfg_split:
+            conf["workload"] = (f"config2 image2video 16-frame window 512x512, {DDIM_STEPS} DDIM steps, CFG, {args.preset} UNet3D; "
+                                f"CFG split over {world} GPUs: {T} frames = {n_windows} window(s)")
         print(json.dumps({
             "metric": METRIC, "value": value, "unit": "frames/s", "n_gpus": world, "steps": args.steps,
-            "warmup": args.warmup, "ms_per_step": ms_total / args.steps, "higher_is_better": True, "scaling": "weak",
+            "warmup": args.warmup, "ms_per_step": ms_total / args.steps, "higher_is_better": True,
+            "scaling": "strong" if args.cfg_split else "weak",
             "vs_baseline": None, "dtype": "f16 (fp32 accumulate)", "data": "synthetic",
-            "config": {"workload": f"config2 image2video 16-frame window 512x512, {DDIM_STEPS} DDIM steps, CFG, "
-                                   f"{args.preset} UNet3D" + ("" if world == 1 else f"; weak scaling: {T} frames = {world} windows (16, overlap 4), 1 per GPU"),
-                       "preset": args.preset, "frames": T, "latent_hw": [LAT_H, LAT_W], "ddim_steps": DDIM_STEPS,
-                       "windows": world, "parallelism": f"windows sharded over {world} GPU(s), 1 NCCL all-reduce/step",
-                       "l2_policy": "per-forward activation working set (~4 GB) >> 126 MB L2; no explicit flush",
-                       "achieved_tflops_whole_step": fl_total * DDIM_STEPS * args.steps * world / (ms_total * 1e-3) / 1e12},
+            "config": conf,
             "e2e": {"value": e2e, "unit": "frames/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h},
             "gpu_launches": int(launches),
             "clocks": sampler.summary(),

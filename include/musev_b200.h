@@ -264,6 +264,27 @@ void mvb_profile_enable(int on);
 /* Synchronises the device, sums the recorded event pairs per category (6 entries each) and clears them. */
 int mvb_profile_collect(double* ms_per_category, long long* scopes_per_category);
 
+/* ------------------------------------------------------------------------------------------------------------------
+ * VAE decode, the step after the path.
+ * Reference: `MusevControlNetPipeline.decode_latents` (musev/pipelines/pipeline_controlnet.py:233-238, called in T-segments
+ * at :2157-2171) -> diffusers `decode_latents` (pipelines/stable_diffusion/pipeline_stable_diffusion_img2img.py:486-495:
+ * latents / scaling_factor, `vae.decode`, image / 2 + 0.5, clamp(0, 1)) -> `AutoencoderKL.decode`
+ * (models/autoencoder_kl.py:275-302: post_quant_conv + `Decoder.forward`, models/vae.py:265-316: conv_in, UNetMidBlock2D
+ * with one single-head attention, 4 UpDecoderBlock2D, GroupNorm + SiLU + conv_out).
+ * The handle is created from an `mvb_config` whose block_out_channels are the VAE's (128, 256, 512, 512 for SD-1.5),
+ * in_channels = latent channels, out_channels = image channels, norm_eps 1e-6; weights by the `AutoencoderKL.state_dict()`
+ * names `post_quant_conv.*` and `decoder.*`. */
+typedef struct mvb_vae_decode_args {
+  const void* latents; int latents_is_f32;   /* [N, latent_channels, h, w] (frames on the batch axis) */
+  int N, h, w;
+  float latent_scale;                        /* multiplies the latents first: 1 / scaling_factor (or 1 for plain vae.decode) */
+  void* out; int out_is_f32;                 /* [N, out_channels, 8h, 8w] */
+  int postprocess;                           /* 1: out = clamp(image / 2 + 0.5, 0, 1) (decode_latents), 0: raw decoder output */
+} mvb_vae_decode_args;
+int mvb_create_vae_decoder(const mvb_config* cfg, int device, mvb_handle** out);
+long long mvb_vae_decode_workspace_bytes(mvb_handle* h, const mvb_vae_decode_args* args);
+int mvb_vae_decode(mvb_handle* h, const mvb_vae_decode_args* args, void* workspace, long long workspace_bytes, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

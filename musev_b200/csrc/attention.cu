@@ -64,24 +64,6 @@ __device__ __forceinline__ void poly_exp2_pair(float a0, float a1, float& p0, fl
   p1 = __int_as_float(__float_as_int(q1) + (__float_as_int(t1) << 23));
 }
 
-// Same polynomial, for arguments that carry the -112 exponent offset of the integer fp16 packing below: returns the fp32
-// BIT PATTERNS, flushed to zero when the result would be below the fp32 normal range (n + 127 <= 0 makes the integer sum
-// negative), so that a probability below 2^-14 becomes an fp16 zero / denormal instead of a clamped 2^-13.
-__device__ __forceinline__ void poly_exp2_pair_bits(float a0, float a1, uint32_t& u0, uint32_t& u1) {
-  const F2 a = f2_make(fmaxf(a0, -160.f), fmaxf(a1, -160.f));
-  const F2 t = f2_add(a, f2_make(12582912.f, 12582912.f));
-  const F2 nf = f2_add(t, f2_make(-12582912.f, -12582912.f));
-  const F2 f = f2_fma(nf, f2_make(-1.f, -1.f), a);
-  F2 q = f2_fma(f, f2_make(0.0551716648f, 0.0551716648f), f2_make(0.242611125f, 0.242611125f));
-  q = f2_fma(q, f, f2_make(0.693260968f, 0.693260968f));
-  q = f2_fma(q, f, f2_make(0.999928057f, 0.999928057f));
-  float q0, q1, t0, t1;
-  f2_get(q, q0, q1);
-  f2_get(t, t0, t1);
-  u0 = (uint32_t)max(__float_as_int(q0) + (__float_as_int(t0) << 23), 0);
-  u1 = (uint32_t)max(__float_as_int(q1) + (__float_as_int(t1) << 23), 0);
-}
-
 __device__ __forceinline__ float fast_exp2(float x) {
   float y;
   asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
@@ -844,7 +826,7 @@ attention_pp_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_consta
       const int valid = j < t0 ? min(128, p.nk[0] - j * 128) : min(128, p.nk[1] - (j - t0) * 128);
       mbar_wait_a(a_bar_s, (uint32_t)j & 1u);
       tc_fence_after();
-      uint32_t v[128];
+      uint32_t v[128];                                  // the whole score row of this thread
       tmem_ld32(tS, *reinterpret_cast<uint32_t(*)[32]>(&v[0]));
       tmem_ld32(tS + 32, *reinterpret_cast<uint32_t(*)[32]>(&v[32]));
       tmem_ld32(tS + 64, *reinterpret_cast<uint32_t(*)[32]>(&v[64]));
@@ -859,49 +841,31 @@ attention_pp_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_consta
           if (i >= valid) v[i] = 0xff800000u;          // -inf
       }
       float mx0 = __uint_as_float(v[0]), mx1 = __uint_as_float(v[1]), mx2 = __uint_as_float(v[2]), mx3 = __uint_as_float(v[3]);
+      float mx4 = __uint_as_float(v[4]), mx5 = __uint_as_float(v[5]), mx6 = __uint_as_float(v[6]), mx7 = __uint_as_float(v[7]);
 #pragma unroll
-      for (int i = 4; i < 124; i += 8) {
+      for (int i = 8; i < 120; i += 16) {               // eight independent FMNMX3 chains (a chain of 16 was latency-bound)
         mx0 = fmax3(mx0, __uint_as_float(v[i]), __uint_as_float(v[i + 1]));
         mx1 = fmax3(mx1, __uint_as_float(v[i + 2]), __uint_as_float(v[i + 3]));
         mx2 = fmax3(mx2, __uint_as_float(v[i + 4]), __uint_as_float(v[i + 5]));
         mx3 = fmax3(mx3, __uint_as_float(v[i + 6]), __uint_as_float(v[i + 7]));
+        mx4 = fmax3(mx4, __uint_as_float(v[i + 8]), __uint_as_float(v[i + 9]));
+        mx5 = fmax3(mx5, __uint_as_float(v[i + 10]), __uint_as_float(v[i + 11]));
+        mx6 = fmax3(mx6, __uint_as_float(v[i + 12]), __uint_as_float(v[i + 13]));
+        mx7 = fmax3(mx7, __uint_as_float(v[i + 14]), __uint_as_float(v[i + 15]));
       }
-      mx0 = fmax3(mx0, __uint_as_float(v[124]), __uint_as_float(v[125]));
-      mx1 = fmax3(mx1, __uint_as_float(v[126]), __uint_as_float(v[127]));
-      const float mx = fmaxf(fmaxf(mx0, mx1), fmaxf(mx2, mx3)) * sl2;
+      mx0 = fmax3(mx0, __uint_as_float(v[120]), __uint_as_float(v[121]));
+      mx1 = fmax3(mx1, __uint_as_float(v[122]), __uint_as_float(v[123]));
+      mx2 = fmax3(mx2, __uint_as_float(v[124]), __uint_as_float(v[125]));
+      mx3 = fmax3(mx3, __uint_as_float(v[126]), __uint_as_float(v[127]));
+      const float mx = fmax3(fmax3(mx0, mx1, mx2), fmax3(mx3, mx4, mx5), fmaxf(mx6, mx7)) * sl2;
       const bool need = mx > m + 8.f;                   // lazy rescale: P stays below 2^8, far inside fp16 range
       float alpha = 1.f;
       if (need) { alpha = fast_exp2(m - mx); m = mx; }
-      // fp32 -> fp16 WITHOUT the conversion instruction: F2FP.F16.F32.PACK_AB issues on the quarter-rate XU pipe next to
-      // MUFU.EX2 (measured: the kernel's time tracked (MUFU + F2FP) x 8 clk per warp instruction exactly), so it cost as
-      // much as two thirds of the exponentials. Instead the exponent offset of the two formats (127 - 15 = 112) is folded
-      // into the exp2 argument -- ex2(x - 112) has fp16's biased exponent in fp32's exponent field, and ex2.approx.ftz
-      // flushes what would be an fp16 denormal -- and the fp16 bit pattern is bits [13, 29) of the result: one shift per
-      // element and one LOP3 per pair on the integer pipe. Truncation instead of round-to-nearest is a common factor
-      // (1 - 2^-12 on average) of numerator and denominator: the row sum is accumulated from the same truncated values.
-      const F2 sl2x2 = f2_make(sl2, sl2), nmx2 = f2_make(-m - 112.f, -m - 112.f);
-      uint32_t pk[64];
-      float ls0 = 0.f, ls1 = 0.f;
-#pragma unroll
-      for (int i = 0; i < 64; ++i) {                    // column pair i; kPolyOf8 of every 8 pairs take the FMA-pipe exp2
-        float a0, a1;
-        f2_get(f2_fma(f2_make(__uint_as_float(v[2 * i]), __uint_as_float(v[2 * i + 1])), sl2x2, nmx2), a0, a1);
-        uint32_t u0, u1;
-        if (((i * kPolyOf8) & 7) < kPolyOf8) {
-          poly_exp2_pair_bits(a0, a1, u0, u1);
-        } else {
-          u0 = __float_as_uint(fast_exp2(a0));
-          u1 = __float_as_uint(fast_exp2(a1));
-        }
-        pk[i] = ((u1 << 3) & 0xffff0000u) | (u0 >> 13);
-        if (!kSumInV) {
-          ls0 += __uint_as_float(u0 & 0xffffe000u);
-          ls1 += __uint_as_float(u1 & 0xffffe000u);
-        }
-      }
-      if (!kSumInV) l = l * alpha + (ls0 + ls1);     // in units of 2^-112
+      // P_t's TMEM columns and O_t are free / final once P_t(j-1) V(j-1) has completed -- issued a whole softmax ago, so
+      // this wait is normally already satisfied. Taking it BEFORE the exponentials lets the P stores below leave chunk by
+      // chunk under the remaining arithmetic instead of all at the end.
       if (j > 0) {
-        mbar_wait_a(a_bar_pv, (uint32_t)(j - 1) & 1u);  // P_t free again and O_t(j-1) final before it is rescaled
+        mbar_wait_a(a_bar_pv, (uint32_t)(j - 1) & 1u);
         tc_fence_after();
         if (__any_sync(0xffffffffu, need)) {
           for (int c0 = 0; c0 < p.dp; c0 += 16) {
@@ -914,8 +878,33 @@ attention_pp_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_consta
           }
         }
       }
-      tmem_st32(tP, *reinterpret_cast<uint32_t(*)[32]>(&pk[0]));
-      tmem_st32(tP + 32, *reinterpret_cast<uint32_t(*)[32]>(&pk[32]));
+      const F2 sl2x2 = f2_make(sl2, sl2), nmx2 = f2_make(-m, -m);
+      float ls0 = 0.f, ls1 = 0.f;
+#pragma unroll
+      for (int c = 0; c < 4; ++c) {                     // 4 chunks of 16 column pairs = one 16-register TMEM store each
+        uint32_t pk[16];
+#pragma unroll
+        for (int e = 0; e < 16; ++e) {
+          const int i = c * 16 + e;                     // column pair i; kPolyOf8 of every 8 pairs take the FMA-pipe exp2
+          float a0, a1;
+          f2_get(f2_fma(f2_make(__uint_as_float(v[2 * i]), __uint_as_float(v[2 * i + 1])), sl2x2, nmx2), a0, a1);
+          float p0, p1;
+          if (((i * kPolyOf8) & 7) < kPolyOf8) {
+            poly_exp2_pair(a0, a1, p0, p1);
+          } else {
+            p0 = fast_exp2(a0);
+            p1 = fast_exp2(a1);
+          }
+          const __half2 hp = __floats2half2_rn(p0, p1);
+          pk[e] = *reinterpret_cast<const uint32_t*>(&hp);
+          if (!kSumInV) {
+            const float2 back = __half22float2(hp);
+            ls0 += back.x; ls1 += back.y;
+          }
+        }
+        tmem_st16(tP + c * 16, pk);
+      }
+      if (!kSumInV) l = l * alpha + (ls0 + ls1);
       tmem_st_wait();
       tc_fence_before();
       __syncwarp();
@@ -929,8 +918,6 @@ attention_pp_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_consta
       tmem_ld16(tO + (p.d / 16) * 16, o);
       tmem_ld_wait();
       l = __uint_as_float(o[p.d % 16 == 8 ? 8 : 0]);     // the ones column of V accumulated the row sum
-    } else {
-      l *= 5.192296858534828e33f;                         // 2^112: the register row sum was kept in the exp2 offset domain
     }
     const float inv = p.out_scale / l;
     const int qrow = q0 + t * 128 + row;
@@ -1062,7 +1049,7 @@ cudaError_t launch_attention(cudaStream_t stream, const AttnArgs& a, const char*
     static const KernelFn pp_kernels[2][4] = {
         {attention_pp_kernel<false, 0>, attention_pp_kernel<false, 2>, attention_pp_kernel<false, 3>, attention_pp_kernel<false, 4>},
         {attention_pp_kernel<true, 0>, attention_pp_kernel<true, 2>, attention_pp_kernel<true, 3>, attention_pp_kernel<true, 4>}};
-    static const int pp_poly_env = getenv("MVB_POLY") ? atoi(getenv("MVB_POLY")) : 3;
+    static const int pp_poly_env = getenv("MVB_POLY") ? atoi(getenv("MVB_POLY")) : 2;
     const int pp_idx = pp_poly_env <= 0 ? 0 : pp_poly_env == 2 ? 1 : pp_poly_env >= 4 ? 3 : 2;
     const int smem_pp = (2 + 2 * kPpStages) * kAtomBytes + 1024 + 512;
     static bool pp_set_dev[64] = {};

@@ -109,6 +109,11 @@ Engine::Engine(const mvb_config& cfg, int device, int kind) : cfg_(cfg), device_
     // musev/models/unet_2d_blocks.py -> musev BasicTransformerBlock and inherits the eps = 0 quirk (Q1)
     ln_eps13_ = kind_ == 1 ? 1e-5f : 0.f;
   }
+  if (kind_ == 3) {
+    cfg_.need_transformer_in = cfg_.use_anivv1_cfg = cfg_.resnet_2d_skip_time_act = cfg_.keep_vision_condtion = 0;
+    cfg_.need_refer_emb = cfg_.ip_adapter_cross_attn = cfg_.need_t2i_ip_adapter = 0;
+    heads_ = 1;
+  }
   cudaSetDevice(device);
   cudaDeviceGetAttribute(&num_sms_, cudaDevAttrMultiProcessorCount, device);
   if (num_sms_ <= 0) num_sms_ = 148;
@@ -241,14 +246,16 @@ void Engine::build_tblock(const std::string& p, TBlock& b, int C, bool cross) {
   reg_linear(p + ".ff.net.2", b.ff2, C, 4 * C, true);
 }
 
-void Engine::build_resnet(const std::string& p, Resnet& r, int cin, int C) {
-  r.cin = cin; r.C = C;
+void Engine::build_resnet(const std::string& p, Resnet& r, int cin, int C, bool has_temb) {
+  r.cin = cin; r.C = C; r.has_temb = has_temb;
   r.n1 = make_norm(p + ".norm1", cin);
   reg_conv(p + ".conv1", r.conv1, C, cin, 9);
   r.temb_off = temb_total_;
-  reg_mat(p + ".time_emb_proj.weight", temb_all_, temb_total_, C, 0, 0, 0, C, cfg_.block_out_channels[0] * 4);
-  reg_vec(p + ".time_emb_proj.bias", temb_all_.bias ? temb_all_.bias + temb_total_ : nullptr, C, C);
-  temb_total_ += C;
+  if (has_temb) {
+    reg_mat(p + ".time_emb_proj.weight", temb_all_, temb_total_, C, 0, 0, 0, C, cfg_.block_out_channels[0] * 4);
+    reg_vec(p + ".time_emb_proj.bias", temb_all_.bias ? temb_all_.bias + temb_total_ : nullptr, C, C);
+    temb_total_ += C;
+  }
   r.n2 = make_norm(p + ".norm2", C);
   reg_conv(p + ".conv2", r.conv2, C, C, 9);
   r.has_shortcut = cin != C;
@@ -299,7 +306,51 @@ void Engine::build_refer(const std::string& p, ReferAttn& r, int C) {
 }
 
 void Engine::build() {
-  if (kind_ == 1 || kind_ == 2) build_controlnet(); else build_unet();
+  if (kind_ == 1 || kind_ == 2) build_controlnet();
+  else if (kind_ == 3) build_vae();
+  else build_unet();
+}
+
+// AutoencoderKL decoder half: post_quant_conv + Decoder.__init__ (diffusers models/autoencoder_kl.py:102-104, vae.py:201-263):
+// conv_in, UNetMidBlock2D (resnet, single-head attention, resnet), one UpDecoderBlock2D per entry of block_out_channels
+// (reversed; layers_per_block + 1 resnets each, nearest-2x + conv upsampler except the last), GroupNorm + SiLU + conv_out.
+void Engine::build_vae() {
+  const mvb_config& c = cfg_;
+  const int nb = c.num_blocks;
+  const int zc = c.in_channels, cm = c.block_out_channels[nb - 1];
+  temb_total_ = femb_total_ = 0;
+  vae_pq_w_ = slab<float>((size_t)zc * zc);
+  vae_pq_b_ = slab<float>(zc);
+  reg_vec("post_quant_conv.weight", vae_pq_w_, zc * zc, zc * zc);
+  reg_vec("post_quant_conv.bias", vae_pq_b_, zc, zc);
+  conv_in_ = make_mat(cm, 64, true);
+  reg_mat("decoder.conv_in.weight", conv_in_, 0, cm, 0, 0, 0, cm, zc * 9, 1, zc, 9);
+  reg_vec("decoder.conv_in.bias", conv_in_.bias, cm, cm);
+  build_resnet("decoder.mid_block.resnets.0", mid_res_[0], cm, cm, false);
+  vae_attn_norm_ = make_norm("decoder.mid_block.attentions.0.group_norm", cm);
+  reg_linear("decoder.mid_block.attentions.0.to_q", vae_q_, cm, cm, true);
+  reg_linear("decoder.mid_block.attentions.0.to_k", vae_k_, cm, cm, true);
+  reg_linear("decoder.mid_block.attentions.0.to_v", vae_v_, cm, cm, true);
+  reg_linear("decoder.mid_block.attentions.0.to_out.0", vae_o_, cm, cm, true);
+  build_resnet("decoder.mid_block.resnets.1", mid_res_[1], cm, cm, false);
+  up_.resize(nb);
+  int ch = cm;
+  for (int i = 0; i < nb; ++i) {
+    const int prev = ch;
+    ch = c.block_out_channels[nb - 1 - i];
+    Block& b = up_[i];
+    b.layers.resize(c.layers_per_block + 1);
+    const std::string p = "decoder.up_blocks." + std::to_string(i);
+    for (int j = 0; j <= c.layers_per_block; ++j)
+      build_resnet(p + ".resnets." + std::to_string(j), b.layers[j].res, j == 0 ? prev : ch, ch, false);
+    b.has_sampler = i != nb - 1;
+    if (b.has_sampler) reg_conv(p + ".upsamplers.0.conv", b.sampler, ch, ch, 9);
+  }
+  const int c0 = c.block_out_channels[0];
+  norm_out_ = make_norm("decoder.conv_norm_out", c0);
+  conv_out_ = make_mat(16, 9 * c0, true);
+  reg_mat("decoder.conv_out.weight", conv_out_, 0, 16, 0, 0, 0, c.out_channels, 9 * c0, 1, c0, 9);
+  reg_vec("decoder.conv_out.bias", conv_out_.bias, 16, c.out_channels);
 }
 
 // ControlNetModel.__init__ (diffusers models/controlnet.py:181-447) minus the conditioning embedding (see header)
@@ -662,7 +713,8 @@ struct Engine::Fwd {
     gn(x, Cx, x1, C1, Hd * Wd, 1, E->cfg_.norm_eps, r.n1, 1, h0);
     __half* h1 = alloc_h(M, r.C);
     Epilogue e1;
-    e1.out = h1; e1.ldc = r.C; e1.rowadd = temb_table + r.temb_off; e1.rows_per_group = Hd * Wd; e1.ld_rowadd = E->temb_total_;
+    e1.out = h1; e1.ldc = r.C;
+    if (r.has_temb) { e1.rowadd = temb_table + r.temb_off; e1.rows_per_group = Hd * Wd; e1.ld_rowadd = E->temb_total_; }
     conv3x3(h0, r.cin, nullptr, 0, NF, Hd, Wd, r.conv1, e1);
     __half* h2 = h0;  // reuse (cin >= C is not guaranteed) -> allocate when it does not fit
     if (r.cin < r.C) h2 = alloc_h(M, r.C);
@@ -1240,6 +1292,145 @@ bool Engine::run_controlnet(const mvb_controlnet_args& a, Arena& ar, cudaStream_
     f.release(mk);
   }
   return f.ok;
+}
+
+// AutoencoderKL.decode (diffusers models/autoencoder_kl.py:275-302) = post_quant_conv + Decoder.forward (models/vae.py:265-316),
+// frames on the batch axis, channels-last activations like the UNet.
+bool Engine::run_vae(const mvb_vae_decode_args& a, Arena& ar, cudaStream_t s) {
+  const mvb_config& c = cfg_;
+  const int nb = c.num_blocks, zc = c.in_channels, cm = c.block_out_channels[nb - 1];
+  const int NF = a.N;
+  if (NF < 1 || a.h < 1 || a.w < 1) { err_ = "vae: bad shape"; return false; }
+  if (((long long)a.h * a.w) % 64 || (long long)a.h * a.w > 8192) {
+    err_ = "vae: latent h*w must be a multiple of 64 and at most 8192 (mid-block attention runs as GEMMs over the tokens)"; return false;
+  }
+  mvb_unet_args ua{};
+  ua.B = NF; ua.T = 1; ua.H = a.h; ua.W = a.w;
+  Fwd f;
+  f.E = this; f.ar = &ar; f.s = s; f.dry = ar.dry; f.a = &ua;
+  f.B = NF; f.T = 1; f.H = a.h; f.W = a.w; f.NF = NF;
+  f.heads = 1;
+  f.skip_temporal = true;
+  f.temb_table = nullptr; f.femb_table = nullptr; f.enc = nullptr; f.clip = nullptr;
+  if (!ar.dry) taps_.clear();
+  f.gn_part = f.alloc_f((long long)NF * (kGnMaxChunks + 1) * c.norm_num_groups * 2);
+  int Hc = a.h, Wc = a.w;
+  const long long M0 = (long long)NF * Hc * Wc;
+  // ---- post_quant_conv + conv_in (autoencoder_kl.py:283, vae.py:268)
+  __half* x = f.alloc_h(M0, cm);
+  {
+    const size_t mk = f.mark();
+    float* z = f.alloc_f((long long)NF * zc * Hc * Wc);
+    __half* A = f.alloc_h(M0, 64);
+    if (!ar.dry && f.ok) {
+      cudaError_t e = latent_pointwise(s, a.latents, a.latents_is_f32, NF, zc, Hc * Wc, vae_pq_w_, vae_pq_b_, a.latent_scale, z);
+      if (e == cudaSuccess) e = im2col_latent(s, z, 1, NF, zc, 1, Hc, Wc, A);
+      if (e != cudaSuccess) f.fail("vae inputs", e);
+    }
+    Epilogue ep; ep.out = x; ep.ldc = cm;
+    f.gemm(A, M0, 64, conv_in_, ep);
+    f.release(mk);
+  }
+  f.tap("conv_in", x, M0, cm);
+  // ---- mid block (unet_2d_blocks.py UNetMidBlock2D: resnet, Attention, resnet)
+  x = f.resnet(mid_res_[0], x, cm, nullptr, 0, Hc, Wc);
+  f.tap("mid.resnets.0", x, M0, cm);
+  {
+    // diffusers Attention with one head of dim cm (attention_processor.py:1166-1250, `residual_connection=True`,
+    // `rescale_output_factor=1`): GroupNorm(eps 1e-6) -> q, k, v (with bias) -> softmax(q k^T / sqrt(cm)) v -> to_out + x.
+    // The head dim (512) is beyond the flash kernels' tile, and the problem is tiny (one 4096-token frame = 2 x 17 GFLOP),
+    // so it runs as two tcgen05 GEMMs per frame around a row-softmax: S = Q K^T with K as the "weight" operand, O = P V
+    // with V^T as the weight operand (produced directly by a GEMM with the roles of W_v and the tokens swapped). The V
+    // bias is added after P V: softmax rows sum to one, so P (V + 1 b^T) = P V + b^T.
+    const int HW = Hc * Wc;
+    __half* out = f.alloc_h(M0, cm);
+    const size_t mk = f.mark();
+    __half* nbuf = f.alloc_h(M0, cm);
+    f.gn(x, cm, nullptr, 0, HW, 1, c.norm_eps, vae_attn_norm_, 0, nbuf);
+    __half* q = f.alloc_h(M0, cm);
+    __half* k = f.alloc_h(M0, cm);
+    { Epilogue ep; ep.out = q; ep.ldc = cm; f.gemm(nbuf, M0, cm, vae_q_, ep); }
+    { Epilogue ep; ep.out = k; ep.ldc = cm; f.gemm(nbuf, M0, cm, vae_k_, ep); }
+    __half* vt = f.alloc_h((long long)NF * cm, HW);         // per frame: V^T [cm, HW]
+    __half* sc = f.alloc_h(HW, HW);                           // one frame's scores / probabilities
+    __half* ao = f.alloc_h(M0, cm);
+    for (int n = 0; n < NF; ++n) {
+      Mat tok; tok.w = nbuf + (long long)n * HW * cm; tok.N = HW; tok.K = cm; tok.bias = nullptr;
+      { Epilogue ep; ep.out = vt + (long long)n * cm * HW; ep.ldc = HW; f.gemm(vae_v_.w, cm, cm, tok, ep, false); }
+      Mat km; km.w = k + (long long)n * HW * cm; km.N = HW; km.K = cm; km.bias = nullptr;
+      { Epilogue ep; ep.out = sc; ep.ldc = HW; f.gemm(q + (long long)n * HW * cm, HW, cm, km, ep, false); }
+      if (!ar.dry && f.ok) {
+        cudaError_t e = softmax_rows(s, sc, HW, HW, HW, 1.f / sqrtf((float)cm));
+        if (e != cudaSuccess) f.fail("softmax_rows", e);
+      }
+      Mat vm; vm.w = vt + (long long)n * cm * HW; vm.N = cm; vm.K = HW; vm.bias = vae_v_.bias;
+      { Epilogue ep; ep.out = ao + (long long)n * HW * cm; ep.ldc = cm; f.gemm(sc, HW, HW, vm, ep, true); }
+    }
+    { Epilogue ep; ep.out = out; ep.ldc = cm; ep.res = x; ep.ld_res = cm; f.gemm(ao, M0, cm, vae_o_, ep); }
+    f.release(mk);
+    x = out;
+  }
+  f.tap("mid.attentions.0", x, M0, cm);
+  x = f.resnet(mid_res_[1], x, cm, nullptr, 0, Hc, Wc);
+  f.tap("mid", x, M0, cm);
+  // ---- up blocks (unet_2d_blocks.py UpDecoderBlock2D)
+  int ch = cm;
+  for (int i = 0; i < nb; ++i) {
+    Block& blk = up_[i];
+    for (size_t j = 0; j < blk.layers.size(); ++j) {
+      x = f.resnet(blk.layers[j].res, x, ch, nullptr, 0, Hc, Wc);
+      ch = blk.layers[j].res.C;
+    }
+    f.tap("up_blocks." + std::to_string(i), x, (long long)NF * Hc * Wc, ch);
+    if (blk.has_sampler) {
+      __half* y = f.alloc_h((long long)NF * 4 * Hc * Wc, ch);
+      const size_t mk = f.mark();
+      __half* up = f.alloc_h((long long)NF * 4 * Hc * Wc, ch);
+      if (!ar.dry && f.ok) {
+        cudaError_t e = upsample2x(s, x, NF, Hc, Wc, ch, up);
+        if (e != cudaSuccess) f.fail("upsample2x", e);
+      }
+      Hc *= 2; Wc *= 2;
+      Epilogue ep; ep.out = y; ep.ldc = ch;
+      f.conv3x3(up, ch, nullptr, 0, NF, Hc, Wc, blk.sampler, ep);
+      f.release(mk);
+      x = y;
+    }
+  }
+  // ---- out (vae.py:307-314)
+  const long long M = (long long)NF * Hc * Wc;
+  __half* hn = f.alloc_h(M, ch);
+  f.gn(x, ch, nullptr, 0, Hc * Wc, 1, c.norm_eps, norm_out_, 1, hn);
+  __half* o16 = f.alloc_h(M, 16);
+  { Epilogue ep; ep.out = o16; ep.ldc = 16; f.conv3x3(hn, ch, nullptr, 0, NF, Hc, Wc, conv_out_, ep); }
+  if (!ar.dry && f.ok) {
+    cudaError_t e = a.postprocess
+        ? tokens_to_ncthw_affine(s, o16, 16, NF, c.out_channels, 1, Hc * Wc, a.out, a.out_is_f32, 0.5f, 0.5f, 0.f, 1.f)
+        : tokens_to_ncthw(s, o16, 16, NF, c.out_channels, 1, Hc * Wc, a.out, a.out_is_f32);
+    if (e != cudaSuccess) f.fail("vae output", e);
+  }
+  return f.ok;
+}
+
+long long Engine::vae_workspace_bytes(const mvb_vae_decode_args& a) {
+  if (kind_ != 3) { err_ = "not a VAE decoder handle"; return -1; }
+  Arena ar;
+  ar.dry = true;
+  if (!run_vae(a, ar, nullptr)) return -1;
+  return (long long)ar.peak + 4096;
+}
+
+int Engine::vae_decode(const mvb_vae_decode_args& a, void* workspace, long long wbytes, cudaStream_t stream) {
+  if (kind_ != 3) { err_ = "not a VAE decoder handle"; return MVB_ERR_STATE; }
+  if (!finalized_) { err_ = "mvb_finalize has not been called (or weights are missing)"; return MVB_ERR_STATE; }
+  if (!a.latents || !a.out || !workspace) { err_ = "null pointer argument"; return MVB_ERR_INVALID; }
+  cudaSetDevice(device_);
+  Arena ar;
+  ar.dry = false;
+  ar.base = (char*)workspace;
+  ar.cap = (size_t)wbytes;
+  if (!run_vae(a, ar, stream)) return MVB_ERR_CUDA;
+  return MVB_OK;
 }
 
 long long Engine::controlnet_workspace_bytes(const mvb_controlnet_args& a) {

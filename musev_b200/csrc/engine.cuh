@@ -36,6 +36,7 @@ struct Resnet {
   Mat conv1, conv2, shortcut;
   int cin = 0, C = 0, temb_off = 0;
   bool has_shortcut = false;
+  bool has_temb = true;    // false in the VAE decoder (temb_channels=None)
 };
 struct TempConv {
   Norm n[4];
@@ -113,7 +114,8 @@ struct Arena {
 class Engine {
  public:
   // kind 0: UNet3DConditionModel; kind 1: ControlNet encoder (diffusers models/controlnet.py);
-  // kind 2: ReferenceNet2D encoder + mid block (musev/models/referencenet.py)
+  // kind 2: ReferenceNet2D encoder + mid block (musev/models/referencenet.py);
+  // kind 3: AutoencoderKL decoder (diffusers models/autoencoder_kl.py, vae.py)
   explicit Engine(const mvb_config& cfg, int device, int kind = 0);
   ~Engine();
   int load_weight(const char* name, const void* dev_ptr, int is_f32, const long long* shape, int ndim);
@@ -121,6 +123,8 @@ class Engine {
   int finalize();
   long long workspace_bytes(const mvb_unet_args& a);
   int forward(const mvb_unet_args& a, void* workspace, long long workspace_bytes, cudaStream_t stream);
+  long long vae_workspace_bytes(const mvb_vae_decode_args& a);
+  int vae_decode(const mvb_vae_decode_args& a, void* workspace, long long workspace_bytes, cudaStream_t stream);
   long long controlnet_workspace_bytes(const mvb_controlnet_args& a);
   int controlnet_forward(const mvb_controlnet_args& a, void* workspace, long long workspace_bytes, cudaStream_t stream);
   int kind() const { return kind_; }
@@ -134,6 +138,7 @@ class Engine {
   void build();
   void build_unet();
   void build_controlnet();
+  void build_vae();
   template <typename T> T* slab(size_t n);
   Mat make_mat(int N, int K, bool bias);
   Norm make_norm(const std::string& p, int C);
@@ -143,7 +148,7 @@ class Engine {
   void reg_linear(const std::string& p, Mat& m, int N, int K, bool bias);
   void reg_conv(const std::string& p, Mat& m, int N, int Cin, int taps);
   void build_tblock(const std::string& p, TBlock& b, int C, bool cross);
-  void build_resnet(const std::string& p, Resnet& r, int cin, int C);
+  void build_resnet(const std::string& p, Resnet& r, int cin, int C, bool has_temb = true);
   void build_tempconv(const std::string& p, TempConv& t, int C);
   void build_spatial(const std::string& p, SpatialT& s, int C);
   void build_temporal(const std::string& p, TemporalT& t, int C);
@@ -153,6 +158,7 @@ class Engine {
   struct Fwd;
   bool run(const mvb_unet_args& a, Arena& ar, cudaStream_t s);
   bool run_controlnet(const mvb_controlnet_args& a, Arena& ar, cudaStream_t s);
+  bool run_vae(const mvb_vae_decode_args& a, Arena& ar, cudaStream_t s);
 
   mvb_config cfg_;
   int device_ = 0, num_sms_ = 148;
@@ -188,6 +194,11 @@ class Engine {
   float* fidx_dev_ = nullptr;    // device float[64] scratch for timestep / frame index values
   Mat zero_convs_[MVB_CONTROLNET_MAX_OUT];   // ControlNet: controlnet_down_blocks.* then controlnet_mid_block
   int n_zero_convs_ = 0;
+  // VAE decoder: post_quant_conv (fp32 [C, C] + bias), single-head mid-block attention (q/k/v/out with bias, GroupNorm)
+  float* vae_pq_w_ = nullptr;
+  float* vae_pq_b_ = nullptr;
+  Norm vae_attn_norm_;
+  Mat vae_q_, vae_k_, vae_v_, vae_o_;
 };
 
 }  // namespace mvb

@@ -631,6 +631,134 @@ cudaError_t expand_rows(cudaStream_t s, const __half* src, int B, int T, int D, 
   return cudaGetLastError();
 }
 
+// ------------------------------------------------------------------------------------------------ VAE decoder helpers
+// post_quant_conv (AutoencoderKL.decode, diffusers models/autoencoder_kl.py:275-287): a 1x1 convolution over the 4 latent
+// channels, applied before the decoder's 3x3 conv_in (whose zero padding acts on ITS input, so the two cannot be folded).
+// y = in_scale * W x + b on [N, C, HW] (NCHW), fp32 out.
+template <typename TIn>
+__global__ void latent_pointwise_kernel(const TIn* __restrict__ x, int N, int C, int HW, const float* __restrict__ w,
+                                        const float* __restrict__ b, float in_scale, float* __restrict__ y) {
+  const long long total = (long long)N * HW;
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+    const long long n = i / HW, p = i % HW;
+    float v[8];
+    for (int k = 0; k < C; ++k) v[k] = (float)x[(n * C + k) * HW + p] * in_scale;
+    for (int c = 0; c < C; ++c) {
+      float acc = b[c];
+      for (int k = 0; k < C; ++k) acc = fmaf(w[c * C + k], v[k], acc);
+      y[(n * C + c) * HW + p] = acc;
+    }
+  }
+}
+cudaError_t latent_pointwise(cudaStream_t s, const void* x, int is_f32, int N, int C, int HW, const float* w, const float* b,
+                             float in_scale, float* y) {
+  ProfScope prof(s, KC_OTHER);
+  if (C > 8) return cudaErrorInvalidValue;
+  const long long total = (long long)N * HW;
+  const int blocks = (int)((total + 255) / 256 < 148 * 8 ? (total + 255) / 256 : 148 * 8);
+  if (is_f32) latent_pointwise_kernel<float><<<blocks, 256, 0, s>>>((const float*)x, N, C, HW, w, b, in_scale, y);
+  else latent_pointwise_kernel<__half><<<blocks, 256, 0, s>>>((const __half*)x, N, C, HW, w, b, in_scale, y);
+  return cudaGetLastError();
+}
+
+// In-place row softmax of an fp16 score matrix [M, N] (N % 8 == 0), fp32 statistics: p = exp(scale (s - max)) / sum. One
+// warp per row, the row held in registers for N <= 8192 (three passes over registers, one read + one write of HBM).
+__global__ void __launch_bounds__(256)
+softmax_rows_kernel(__half* __restrict__ x, long long M, int N, long long ld, float scale_log2) {
+  const long long row = (long long)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  if (row >= M) return;
+  const int lane = threadIdx.x & 31;
+  __half* r = x + row * ld;
+  const int vecs = N / 8;
+  constexpr int kMaxV = 32;                      // 32 lanes x 32 vectors x 8 = 8192 columns
+  Half8 hv[kMaxV];
+  float mx = -INFINITY;
+#pragma unroll
+  for (int i = 0; i < kMaxV; ++i) {
+    const int vi = lane + i * 32;
+    if (vi < vecs) {
+      hv[i] = ld_half8(r + vi * 8);
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        const float2 t = __half22float2(hv[i].h[j]);
+        mx = fmaxf(mx, fmaxf(t.x, t.y));
+      }
+    }
+  }
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, o));
+  float sum = 0.f;
+  const float nm = -mx * scale_log2;
+#pragma unroll
+  for (int i = 0; i < kMaxV; ++i) {
+    const int vi = lane + i * 32;
+    if (vi < vecs) {
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        float2 t = __half22float2(hv[i].h[j]);
+        asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(t.x) : "f"(fmaf(t.x, scale_log2, nm)));
+        asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(t.y) : "f"(fmaf(t.y, scale_log2, nm)));
+        const __half2 h2 = __floats2half2_rn(t.x, t.y);
+        hv[i].h[j] = h2;
+        const float2 back = __half22float2(h2);    // normalise by the sum of what will actually be multiplied
+        sum += back.x + back.y;
+      }
+    }
+  }
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) sum += __shfl_xor_sync(0xffffffffu, sum, o);
+  const float inv = 1.f / sum;
+#pragma unroll
+  for (int i = 0; i < kMaxV; ++i) {
+    const int vi = lane + i * 32;
+    if (vi < vecs) {
+      Half8 ov;
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        const float2 t = __half22float2(hv[i].h[j]);
+        ov.h[j] = __floats2half2_rn(t.x * inv, t.y * inv);
+      }
+      st_half8(r + vi * 8, ov);
+    }
+  }
+}
+cudaError_t softmax_rows(cudaStream_t s, __half* x, long long M, int N, long long ld, float scale) {
+  ProfScope prof(s, KC_OTHER);
+  if ((N % 8) || N > 8192 || (ld % 8)) return cudaErrorInvalidValue;
+  const unsigned blocks = (unsigned)((M + 7) / 8);
+  softmax_rows_kernel<<<blocks, 256, 0, s>>>(x, M, N, ld, scale * 1.4426950408889634f);
+  return cudaGetLastError();
+}
+
+// tokens [B*T*HW, ldx] -> NCTHW with y = clamp(alpha x + beta, lo, hi): the image post-processing of `decode_latents`
+// (diffusers pipeline_stable_diffusion_img2img.py:490-492: image / 2 + 0.5, clamp(0, 1)) folded into the layout change.
+template <typename TOut>
+__global__ void tokens_to_ncthw_affine_kernel(const __half* __restrict__ x, int ldx, int B, int C, int T, int HW,
+                                              TOut* __restrict__ y, float alpha, float beta, float lo, float hi) {
+  __shared__ float tile[32][33];
+  const int bt = blockIdx.z;
+  const int b = bt / T, t = bt % T;
+  const int p0 = blockIdx.x * 32, c0 = blockIdx.y * 32;
+  for (int py = threadIdx.y; py < 32; py += blockDim.y) {
+    const int p = p0 + py, c = c0 + threadIdx.x;
+    if (c < C && p < HW) tile[py][threadIdx.x] = __half2float(x[((size_t)bt * HW + p) * ldx + c]);
+  }
+  __syncthreads();
+  for (int cy = threadIdx.y; cy < 32; cy += blockDim.y) {
+    const int c = c0 + cy, p = p0 + threadIdx.x;
+    if (c < C && p < HW) y[(((size_t)b * C + c) * T + t) * HW + p] = (TOut)fminf(fmaxf(fmaf(tile[threadIdx.x][cy], alpha, beta), lo), hi);
+  }
+}
+cudaError_t tokens_to_ncthw_affine(cudaStream_t s, const __half* x, int ldx, int B, int C, int T, int HW, void* y, int is_f32,
+                                   float alpha, float beta, float lo, float hi) {
+  ProfScope prof(s, KC_OTHER);
+  dim3 grid((HW + 31) / 32, (C + 31) / 32, B * T), block(32, 8);
+  if (grid.x > 65535u * 32u) return cudaErrorInvalidValue;
+  if (is_f32) tokens_to_ncthw_affine_kernel<float><<<grid, block, 0, s>>>(x, ldx, B, C, T, HW, (float*)y, alpha, beta, lo, hi);
+  else tokens_to_ncthw_affine_kernel<__half><<<grid, block, 0, s>>>(x, ldx, B, C, T, HW, (__half*)y, alpha, beta, lo, hi);
+  return cudaGetLastError();
+}
+
 // ------------------------------------------------------------------------------------------------ temporal attention
 // ---- tensor-core version: one warp per (batch, pixel, head); T <= 32 frames padded to a 32x32 score tile.
 // S = Q K^T and O = P V run on mma.sync m16n8k16 (the problem is 32 x 32 x dp per warp: far too small for tcgen05's

@@ -41,6 +41,13 @@ cudaError_t sinusoid(cudaStream_t s, const float* values, int n, int dim, __half
 cudaError_t expand_rows(cudaStream_t s, const __half* src, int B, int T, int D, const int* zero_t, int nzero, int act,
                         __half* out);
 cudaError_t silu_copy(cudaStream_t s, const __half* x, long long n, __half* y);
+// VAE decoder helpers: post_quant 1x1 conv on the latent channels, in-place row softmax, output layout change with the
+// image post-processing affine + clamp
+cudaError_t latent_pointwise(cudaStream_t s, const void* x, int is_f32, int N, int C, int HW, const float* w, const float* b,
+                             float in_scale, float* y);
+cudaError_t softmax_rows(cudaStream_t s, __half* x, long long M, int N, long long ld, float scale);
+cudaError_t tokens_to_ncthw_affine(cudaStream_t s, const __half* x, int ldx, int B, int C, int T, int HW, void* y, int is_f32,
+                                   float alpha, float beta, float lo, float hi);
 // temporal self-attention over the frame axis (musev/models/temporal_transformer.py:241-273 -> SDPA):
 // qkv [B, T, HW, 3*heads*dp] (q | k | v, head-padded), out [B, T, HW, heads*d].
 cudaError_t temporal_attention(cudaStream_t s, const __half* qkv, int ld, int B, int T, int HW, int heads, int d,

@@ -14,8 +14,9 @@ from typing import Dict, List, Optional, Tuple
 
 import torch
 
-from .schema import (ControlNetConfig, ImageProjConfig, ReferenceNetConfig, UNetConfig, controlnet_param_shapes,
-                     image_proj_param_shapes, refer_emb_shapes, referencenet_param_shapes, unet_param_shapes)
+from .schema import (ControlNetConfig, ImageProjConfig, ReferenceNetConfig, UNetConfig, VAEConfig, controlnet_param_shapes,
+                     image_proj_param_shapes, refer_emb_shapes, referencenet_param_shapes, unet_param_shapes,
+                     vae_decoder_param_shapes)
 
 _BRANCH_OUT = ("conv2.weight", "proj_out.weight", "to_out.0.weight", "ff.net.2.weight", "conv4.3.weight")
 # the ControlNet's zero-initialised convolutions (controlnet.py:97-99,425-444) are drawn non-zero for the same reason
@@ -37,6 +38,8 @@ def make_state_dict(cfg, seed: int = 0, dtype: torch.dtype = torch.float32) -> "
         shapes = controlnet_param_shapes(cfg)
     elif isinstance(cfg, ImageProjConfig):
         shapes = image_proj_param_shapes(cfg)
+    elif isinstance(cfg, VAEConfig):
+        shapes = vae_decoder_param_shapes(cfg)
     else:
         shapes = unet_param_shapes(cfg)
     for name, shape in shapes.items():

@@ -17,8 +17,8 @@ import torch
 
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, ROOT)
-from musev_b200.schema import (ControlNetConfig, ReferenceNetConfig, controlnet_param_shapes, preset_config,  # noqa: E402
-                               referencenet_param_shapes, unet_param_shapes)
+from musev_b200.schema import (ControlNetConfig, ReferenceNetConfig, VAEConfig, controlnet_param_shapes,  # noqa: E402
+                               preset_config, referencenet_param_shapes, unet_param_shapes, vae_decoder_param_shapes)
 from musev_b200.synth import make_controlnet_inputs, make_inputs, make_referencenet_inputs, make_state_dict  # noqa: E402
 from oracle import ref_shim  # noqa: E402
 from oracle.pipeline_oracle import SD15_DDIM  # noqa: E402
@@ -158,6 +158,40 @@ def golden_ddim():
     print("ddim_sd15.pt timesteps", sched.timesteps.tolist())
 
 
+def golden_vae(boc, tag, frames, h, w, wseed=11, iseed=1357):
+    """The unmodified diffusers `AutoencoderKL.decode` (vendored fork) + the pipeline's decode_latents post-processing
+    (pipeline_stable_diffusion_img2img.py:490-492) on seeded decoder weights; 2048 seeded sample positions of the image."""
+    ref_shim.load()
+    from diffusers.models.autoencoder_kl import AutoencoderKL
+    cfg = VAEConfig(block_out_channels=tuple(boc))
+    kw = dict(in_channels=3, out_channels=3, down_block_types=("DownEncoderBlock2D",) * 4, up_block_types=("UpDecoderBlock2D",) * 4,
+              block_out_channels=tuple(boc), layers_per_block=2, act_fn="silu", latent_channels=4, norm_num_groups=32,
+              sample_size=512, scaling_factor=0.18215)
+    t0 = time.time()
+    m = AutoencoderKL(**kw).eval()
+    ref_shapes = {k: tuple(v.shape) for k, v in m.state_dict().items() if k.startswith(("decoder.", "post_quant_conv."))}
+    mine = {k: tuple(v) for k, v in vae_decoder_param_shapes(cfg).items()}
+    assert ref_shapes == mine, "VAE decoder schema mismatch vs reference state_dict"
+    sd = make_state_dict(cfg, seed=wseed)
+    res = m.load_state_dict(sd, strict=False)
+    assert not res.unexpected_keys and all(k.startswith(("encoder.", "quant_conv.")) for k in res.missing_keys)
+    g = torch.Generator().manual_seed(iseed)
+    latents = torch.randn(1, 4, frames, h, w, generator=g) * 0.18215 * 1.2
+    with torch.no_grad():
+        z = latents.permute(0, 2, 1, 3, 4).reshape(frames, 4, h, w) / 0.18215
+        raw = m.decode(z, return_dict=False)[0]
+        img = (raw / 2 + 0.5).clamp(0, 1)
+    flat_raw, flat_img = raw.reshape(-1), img.reshape(-1)
+    idx = torch.randint(0, flat_raw.numel(), (2048,), generator=torch.Generator().manual_seed(3000))
+    meta = dict(block_out_channels=list(boc), frames=frames, h=h, w=w, weight_seed=wseed, input_seed=iseed,
+                shape=list(raw.shape), sample_seed=3000, n_samples=2048,
+                source="reference diffusers.models.autoencoder_kl.AutoencoderKL.decode (vendored fork), CPU fp32")
+    path = os.path.join(GOLDEN, f"vae_{tag}.pt")
+    torch.save({"meta": meta, "raw": flat_raw[idx].clone(), "img": flat_img[idx].clone(),
+                "stats": [float(raw.mean()), float(raw.abs().mean()), float(img.mean())]}, path)
+    print(f"{path}: raw abs-mean {float(raw.abs().mean()):.4f} img mean {float(img.mean()):.4f} ({time.time() - t0:.1f}s)", flush=True)
+
+
 def golden_samplers():
     """The imported musev Euler / LCM schedulers (musev/schedulers/scheduling_{euler_discrete,lcm}.py) on the SD-1.5
     scheduler config: timesteps, sigmas, init_noise_sigma and a full deterministic loop (model = sample * t / (t + 1))."""
@@ -291,6 +325,11 @@ if __name__ == "__main__":
     args = ap.parse_args()
     os.makedirs(GOLDEN, exist_ok=True)
     torch.set_num_threads(os.cpu_count() or 1)
+    if args.only == "vae":
+        golden_vae((64, 64, 128, 128), "narrow", frames=2, h=8, w=8)
+        if args.full:
+            golden_vae((128, 256, 512, 512), "full", frames=1, h=8, w=8)
+        sys.exit(0)
     if args.only == "samplers":
         golden_samplers()
         sys.exit(0)
@@ -317,7 +356,9 @@ if __name__ == "__main__":
     golden_controlnet(NARROW, "narrow_guess", frames=2, h=8, w=8, t=301, scale=1.0, guess=True)
     golden_referencenet(NARROW, "narrow", batch=2, n_ref=1, h=16, w=16)
     golden_referencenet(NARROW, "narrow_t2", batch=1, n_ref=2, h=8, w=8)
+    golden_vae((64, 64, 128, 128), "narrow", frames=2, h=8, w=8)
     if args.full:
+        golden_vae((128, 256, 512, 512), "full", frames=1, h=8, w=8)
         golden_referencenet(FULL, "full", batch=2, n_ref=1, h=8, w=8)
         for preset in ("musev", "musev_referencenet"):
             m, cfg, sd = golden_unet(preset, FULL, "full", batch=2, frames=2, h=8, w=8, t=601)

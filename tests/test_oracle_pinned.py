@@ -253,3 +253,23 @@ def test_sampler_oracles_match_imported_musev_schedulers():
     for i, t in enumerate(l.timesteps):
         x, den, _ = l.step(x * t / (t + 1), t, x, gen)
         assert (x - g["lcm"]["trace"][i]).abs().max().item() < 1e-5 and (den - g["lcm"]["denoised"][i]).abs().max().item() < 1e-5
+
+
+@pytest.mark.parametrize("tag", ["narrow", "full"])
+def test_vae_oracle_matches_reference_golden(tag):
+    """oracle/vae_oracle.py against samples of the unmodified diffusers AutoencoderKL.decode (oracle/make_golden.py)."""
+    from musev_b200.schema import VAEConfig
+    from oracle.vae_oracle import VAEDecoderOracle
+    g = torch.load(os.path.join(GOLDEN, f"vae_{tag}.pt"))
+    m = g["meta"]
+    cfg = VAEConfig(block_out_channels=tuple(m["block_out_channels"]))
+    o = VAEDecoderOracle(cfg, make_state_dict(cfg, seed=m["weight_seed"]))
+    lat = torch.randn(1, 4, m["frames"], m["h"], m["w"], generator=torch.Generator().manual_seed(m["input_seed"])) * 0.18215 * 1.2
+    z = lat.permute(0, 2, 1, 3, 4).reshape(m["frames"], 4, m["h"], m["w"]) / cfg.scaling_factor
+    raw = o.decode(z)
+    assert list(raw.shape) == m["shape"]
+    idx = torch.randint(0, raw.numel(), (m["n_samples"],), generator=torch.Generator().manual_seed(m["sample_seed"]))
+    assert (raw.reshape(-1)[idx] - g["raw"]).abs().max().item() < 2e-5
+    img = o.decode_latents(lat)                                   # [1, 3, f, H, W]
+    flat = img.permute(0, 2, 1, 3, 4).reshape(-1)
+    assert (flat[idx] - g["img"]).abs().max().item() < 2e-5
