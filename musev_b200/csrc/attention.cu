@@ -765,49 +765,69 @@ attention_pp_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_consta
       __syncwarp();
     }
   } else if (warp == 1) {
-    // ---- MMA issuer (warp-uniform loop, one elected lane issues)
+    // ---- MMA issuer: warp-uniform, one elected lane issues. Work items are S_t(j) = Q_t K(j)^T and O_t += P_t(j) V(j) for
+    // the two tiles t. They are issued in READINESS order, polled with non-blocking mbarrier probes, not in a fixed
+    // round-robin: a fixed order (S0, PV0, S1, PV1) makes every wait for one tile's softmax also delay the other tile's
+    // next S, and the ncu source view showed the softmax warps spending 27 % of their samples waiting for S and 9 % for
+    // P.V. Priority: S first (it unblocks a whole softmax iteration), then P.V.
     const uint32_t idesc_s = make_idesc_f16(128, 128, 0, 0);
     const uint32_t idesc_o = make_idesc_f16(128, p.dp, 0, 1);   // B (= V) is MN-major
     const int ksteps = p.dp / 16;
     mbar_wait(bar_q, 0);
-    auto issue_s = [&](int t, int j) {        // S_t(j) = Q_t K(j)^T
-      const int st = j % kPpStages;
-      if (t == 0) mbar_wait(&full_k[st], (uint32_t)(j / kPpStages) & 1u);
-      tc_fence_after();
-      const uint32_t aQ = smem_u32(sQ + t * kAtomBytes);
-      const uint32_t aK = smem_u32(sK + st * kAtomBytes);
-      if (elect_one()) {
-        for (int kk = 0; kk < ksteps; ++kk)
-          umma_f16_ss(tmem_base + (uint32_t)t * 128u, make_desc_k_sw128(aQ + (uint32_t)kk * 32u),
-                      make_desc_k_sw128(aK + (uint32_t)kk * 32u), idesc_s, kk != 0);
-        umma_commit(&bar_s[t]);
-        if (t == 1) umma_commit(&empty_k[st]);   // both tiles have read this K stage
-      }
-      __syncwarp();
-    };
-    issue_s(0, 0);
-    issue_s(1, 0);
-    for (int j = 0; j < ntiles; ++j) {
-      const int st = j % kPpStages;
-      for (int t = 0; t < 2; ++t) {
-        if (j + 1 < ntiles) {
-          mbar_wait(&bar_sfree[t], (uint32_t)j & 1u);   // S_t(j) is in registers: its TMEM tile may be overwritten
-          issue_s(t, j + 1);
-        }
-        if (t == 0) mbar_wait(&full_v[st], (uint32_t)(j / kPpStages) & 1u);
-        mbar_wait(&bar_p[t], (uint32_t)j & 1u);         // P_t(j) in TMEM, O_t rescaled
-        tc_fence_after();
-        const uint32_t aV = smem_u32(sV + st * kAtomBytes);
-        if (elect_one()) {
+    int ns[2] = {0, 0};          // next S tile to issue per query tile
+    int npv[2] = {0, 0};         // next P.V tile to issue per query tile
+    uint32_t spins = 0;
+    while (npv[0] < ntiles || npv[1] < ntiles) {
+      bool progressed = false;
 #pragma unroll
-          for (int k16 = 0; k16 < 8; ++k16)
-            umma_f16_ts(tmem_base + 384u + (uint32_t)t * 64u, tmem_base + 256u + (uint32_t)t * 64u + (uint32_t)k16 * 8u,
-                        make_desc_mn_sw128(aV + (uint32_t)k16 * 2048u, kAtomBytes), idesc_o, (j | k16) != 0);
-          umma_commit(&bar_pv[t]);
-          if (t == 1) umma_commit(&empty_v[st]);
+      for (int t = 0; t < 2; ++t) {
+        // S_t(j): needs K(j) in smem and, for j > 0, S_t(j-1) pulled into registers by the softmax warps
+        const int j = ns[t];
+        if (j < ntiles) {
+          const int st = j % kPpStages;
+          if (mbar_try_wait(&full_k[st], (uint32_t)(j / kPpStages) & 1u) &&
+              (j == 0 || mbar_try_wait(&bar_sfree[t], (uint32_t)(j - 1) & 1u))) {
+            tc_fence_after();
+            const uint32_t aQ = smem_u32(sQ + t * kAtomBytes);
+            const uint32_t aK = smem_u32(sK + st * kAtomBytes);
+            if (elect_one()) {
+              for (int kk = 0; kk < ksteps; ++kk)
+                umma_f16_ss(tmem_base + (uint32_t)t * 128u, make_desc_k_sw128(aQ + (uint32_t)kk * 32u),
+                            make_desc_k_sw128(aK + (uint32_t)kk * 32u), idesc_s, kk != 0);
+              umma_commit(&bar_s[t]);
+              if (ns[t ^ 1] > j) umma_commit(&empty_k[st]);   // the other tile has already read this K stage: release it
+            }
+            __syncwarp();
+            ns[t] = j + 1;
+            progressed = true;
+          }
         }
-        __syncwarp();
       }
+#pragma unroll
+      for (int t = 0; t < 2; ++t) {
+        // O_t += P_t(j) V(j): needs V(j) in smem and P_t(j) in TMEM (which implies O_t rescaled)
+        const int j = npv[t];
+        if (j < ntiles) {
+          const int st = j % kPpStages;
+          if (mbar_try_wait(&full_v[st], (uint32_t)(j / kPpStages) & 1u) && mbar_try_wait(&bar_p[t], (uint32_t)j & 1u)) {
+            tc_fence_after();
+            const uint32_t aV = smem_u32(sV + st * kAtomBytes);
+            if (elect_one()) {
+#pragma unroll
+              for (int k16 = 0; k16 < 8; ++k16)
+                umma_f16_ts(tmem_base + 384u + (uint32_t)t * 64u, tmem_base + 256u + (uint32_t)t * 64u + (uint32_t)k16 * 8u,
+                            make_desc_mn_sw128(aV + (uint32_t)k16 * 2048u, kAtomBytes), idesc_o, (j | k16) != 0);
+              umma_commit(&bar_pv[t]);
+              if (npv[t ^ 1] > j) umma_commit(&empty_v[st]);  // both tiles have consumed this V stage
+            }
+            __syncwarp();
+            npv[t] = j + 1;
+            progressed = true;
+          }
+        }
+      }
+      if (progressed) spins = 0;
+      else if (++spins > (1u << 26)) __trap();      // a protocol bug must not hang the GPU box
     }
   } else {
     // ---- softmax warpgroup t: one thread per query row of tile t
@@ -822,6 +842,14 @@ attention_pp_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_consta
                    a_bar_pv = smem_u32(&bar_pv[t]);
     float m = -INFINITY, l = 0.f;
     const float sl2 = p.scale_log2;
+    // The warp of tile 0 and the warp of tile 1 with the same lane quarter share one SM sub-partition and its SFU. Left
+    // alone they drift into the exponential phase together, halve each other's SFU rate and then both sit in their
+    // load / max / store phases with the SFU idle (measured: 1313 clk per tile against a 768 clk SFU bound). A token
+    // passed through two named barriers per quarter makes the exponential phases ALTERNATE: while one warp owns the SFU
+    // the other does its tcgen05.ld, row max, rescale and P stores -- the ordering FlashAttention-4 imposes between its
+    // two softmax warpgroups. Tile 1 hands the first token to tile 0.
+    const int bar_mine = 1 + qd * 2 + t, bar_other = 1 + qd * 2 + (t ^ 1);
+    if (t == 1) named_bar_arrive(bar_other, 64);
     for (int j = 0; j < ntiles; ++j) {
       const int valid = j < t0 ? min(128, p.nk[0] - j * 128) : min(128, p.nk[1] - (j - t0) * 128);
       mbar_wait_a(a_bar_s, (uint32_t)j & 1u);
@@ -880,6 +908,7 @@ attention_pp_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_consta
       }
       const F2 sl2x2 = f2_make(sl2, sl2), nmx2 = f2_make(-m, -m);
       float ls0 = 0.f, ls1 = 0.f;
+      named_bar_sync(bar_mine, 64);                     // my turn on the SFU
 #pragma unroll
       for (int c = 0; c < 4; ++c) {                     // 4 chunks of 16 column pairs = one 16-register TMEM store each
         uint32_t pk[16];
@@ -904,12 +933,14 @@ attention_pp_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_consta
         }
         tmem_st16(tP + c * 16, pk);
       }
+      named_bar_arrive(bar_other, 64);                  // the other tile's warp may start its exponentials
       if (!kSumInV) l = l * alpha + (ls0 + ls1);
       tmem_st_wait();
       tc_fence_before();
       __syncwarp();
       if (lane == 0) mbar_arrive_a(a_bar_p);
     }
+    if (t == 0) named_bar_sync(bar_mine, 64);           // consume the last token so that no arrival is left pending
     // ---- epilogue: O_t row / row sum -> global
     mbar_wait_a(a_bar_pv, (uint32_t)(ntiles - 1) & 1u);
     tc_fence_after();
