@@ -99,6 +99,13 @@ int mvb_op_temporal_attention(const void* qkv, int ld, int B, int T, int HW, int
 int mvb_op_groupnorm(const void* x0, int c0, const void* x1, int c1, int NF, int HW, int groups, int frames_per_stat,
                      float eps, const float* gamma, const float* beta, int silu, void* y, float* scratch, void* stream);
 
+/* The same GroupNorm as ONE persistent launch (statistics, finalize and apply separated by grid barriers; the engine's
+ * default path). `barrier_word`: a zero-initialised device uint32 owned by the caller; `*arrivals`: host-side count of the
+ * arrivals that word has seen, updated by the call (calls sharing a word must be issued on one stream). */
+int mvb_op_groupnorm_fused(const void* x0, int c0, const void* x1, int c1, int NF, int HW, int groups, int frames_per_stat,
+                           float eps, const float* gamma, const float* beta, int silu, void* y, float* scratch,
+                           unsigned int* barrier_word, unsigned int* arrivals, void* stream);
+
 /* LayerNorm over the channel axis of [M, C] fp16 (F.layer_norm at musev/models/attention.py:193,346-350,399). */
 int mvb_op_layernorm(const void* x, long long M, int C, float eps, const float* gamma, const float* beta, void* y,
                      void* stream);

@@ -69,6 +69,10 @@ def _declare(l: C.CDLL) -> None:
     l.mvb_op_groupnorm.argtypes = [C.c_void_p, C.c_int, C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int,
                                    C.c_float, C.c_void_p, C.c_void_p, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p]
     l.mvb_op_groupnorm.restype = C.c_int
+    l.mvb_op_groupnorm_fused.argtypes = [C.c_void_p, C.c_int, C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int,
+                                         C.c_float, C.c_void_p, C.c_void_p, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p,
+                                         C.POINTER(C.c_uint), C.c_void_p]
+    l.mvb_op_groupnorm_fused.restype = C.c_int
     l.mvb_op_layernorm.argtypes = [C.c_void_p, C.c_longlong, C.c_int, C.c_float, C.c_void_p, C.c_void_p, C.c_void_p,
                                    C.c_void_p]
     l.mvb_op_layernorm.restype = C.c_int

@@ -41,6 +41,8 @@ struct AttnParams {
   long long ldo;
   int accumulate;
   int sum_in_v;   // V has a column of ones at index d (d % 8 == 0, d < dp): the PV MMA accumulates the softmax row sum
+  int pp_order;       // ping-pong kernel, MMA issue order: 0 = S0 S1 PV0 PV1 (default), 1 = S0 PV0 S1 PV1 (A/B runs)
+  int pp_alternate;   // ping-pong kernel: alternate the exponential phases of the two softmax warpgroups (named-barrier token)
 };
 
 static constexpr int kAtomBytes = 128 * 128;  // 128 rows x 64 fp16
@@ -765,69 +767,69 @@ attention_pp_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_consta
       __syncwarp();
     }
   } else if (warp == 1) {
-    // ---- MMA issuer: warp-uniform, one elected lane issues. Work items are S_t(j) = Q_t K(j)^T and O_t += P_t(j) V(j) for
-    // the two tiles t. They are issued in READINESS order, polled with non-blocking mbarrier probes, not in a fixed
-    // round-robin: a fixed order (S0, PV0, S1, PV1) makes every wait for one tile's softmax also delay the other tile's
-    // next S, and the ncu source view showed the softmax warps spending 27 % of their samples waiting for S and 9 % for
-    // P.V. Priority: S first (it unblocks a whole softmax iteration), then P.V.
+    // ---- MMA issuer (warp-uniform loop, one elected lane issues), blocking mbarrier waits. Issue order per KV tile j
+    // (p.pp_order): 1 (default) = S_0(j+1), P_0(j) V(j), S_1(j+1), P_1(j) V(j); 0 = both S first, then both P.V.
+    // Measured on one box (level 0, 20 launches each): order 1 2.884 ms, order 0 2.948 ms (3.39 ms without the SFU token
+    // below). A third variant that polled all four conditions with non-blocking probes and issued in readiness order was
+    // 50 % SLOWER: the spinning MMA warp starves the two softmax warps that share its scheduler.
     const uint32_t idesc_s = make_idesc_f16(128, 128, 0, 0);
     const uint32_t idesc_o = make_idesc_f16(128, p.dp, 0, 1);   // B (= V) is MN-major
     const int ksteps = p.dp / 16;
     mbar_wait(bar_q, 0);
-    int ns[2] = {0, 0};          // next S tile to issue per query tile
-    int npv[2] = {0, 0};         // next P.V tile to issue per query tile
-    uint32_t spins = 0;
-    while (npv[0] < ntiles || npv[1] < ntiles) {
-      bool progressed = false;
+    auto issue_s = [&](int t, int j) {        // S_t(j) = Q_t K(j)^T
+      const int st = j % kPpStages;
+      if (t == 0) mbar_wait(&full_k[st], (uint32_t)(j / kPpStages) & 1u);
+      tc_fence_after();
+      const uint32_t aQ = smem_u32(sQ + t * kAtomBytes);
+      const uint32_t aK = smem_u32(sK + st * kAtomBytes);
+      if (elect_one()) {
+        for (int kk = 0; kk < ksteps; ++kk)
+          umma_f16_ss(tmem_base + (uint32_t)t * 128u, make_desc_k_sw128(aQ + (uint32_t)kk * 32u),
+                      make_desc_k_sw128(aK + (uint32_t)kk * 32u), idesc_s, kk != 0);
+        umma_commit(&bar_s[t]);
+        if (t == 1) umma_commit(&empty_k[st]);   // both tiles have read this K stage
+      }
+      __syncwarp();
+    };
+    issue_s(0, 0);
+    issue_s(1, 0);
+    auto issue_pv = [&](int t, int j) {       // O_t += P_t(j) V(j)
+      const int st = j % kPpStages;
+      if (t == 0) mbar_wait(&full_v[st], (uint32_t)(j / kPpStages) & 1u);
+      mbar_wait(&bar_p[t], (uint32_t)j & 1u);           // P_t(j) in TMEM, O_t rescaled
+      tc_fence_after();
+      const uint32_t aV = smem_u32(sV + st * kAtomBytes);
+      if (elect_one()) {
 #pragma unroll
-      for (int t = 0; t < 2; ++t) {
-        // S_t(j): needs K(j) in smem and, for j > 0, S_t(j-1) pulled into registers by the softmax warps
-        const int j = ns[t];
-        if (j < ntiles) {
-          const int st = j % kPpStages;
-          if (mbar_try_wait(&full_k[st], (uint32_t)(j / kPpStages) & 1u) &&
-              (j == 0 || mbar_try_wait(&bar_sfree[t], (uint32_t)(j - 1) & 1u))) {
-            tc_fence_after();
-            const uint32_t aQ = smem_u32(sQ + t * kAtomBytes);
-            const uint32_t aK = smem_u32(sK + st * kAtomBytes);
-            if (elect_one()) {
-              for (int kk = 0; kk < ksteps; ++kk)
-                umma_f16_ss(tmem_base + (uint32_t)t * 128u, make_desc_k_sw128(aQ + (uint32_t)kk * 32u),
-                            make_desc_k_sw128(aK + (uint32_t)kk * 32u), idesc_s, kk != 0);
-              umma_commit(&bar_s[t]);
-              if (ns[t ^ 1] > j) umma_commit(&empty_k[st]);   // the other tile has already read this K stage: release it
-            }
-            __syncwarp();
-            ns[t] = j + 1;
-            progressed = true;
+        for (int k16 = 0; k16 < 8; ++k16)
+          umma_f16_ts(tmem_base + 384u + (uint32_t)t * 64u, tmem_base + 256u + (uint32_t)t * 64u + (uint32_t)k16 * 8u,
+                      make_desc_mn_sw128(aV + (uint32_t)k16 * 2048u, kAtomBytes), idesc_o, (j | k16) != 0);
+        umma_commit(&bar_pv[t]);
+        if (t == 1) umma_commit(&empty_v[st]);
+      }
+      __syncwarp();
+    };
+    if (p.pp_order == 0) {
+      for (int j = 0; j < ntiles; ++j) {
+        if (j + 1 < ntiles) {
+          for (int t = 0; t < 2; ++t) {
+            mbar_wait(&bar_sfree[t], (uint32_t)j & 1u);   // S_t(j) is in registers: its TMEM tile may be overwritten
+            issue_s(t, j + 1);
           }
         }
+        issue_pv(0, j);
+        issue_pv(1, j);
       }
-#pragma unroll
-      for (int t = 0; t < 2; ++t) {
-        // O_t += P_t(j) V(j): needs V(j) in smem and P_t(j) in TMEM (which implies O_t rescaled)
-        const int j = npv[t];
-        if (j < ntiles) {
-          const int st = j % kPpStages;
-          if (mbar_try_wait(&full_v[st], (uint32_t)(j / kPpStages) & 1u) && mbar_try_wait(&bar_p[t], (uint32_t)j & 1u)) {
-            tc_fence_after();
-            const uint32_t aV = smem_u32(sV + st * kAtomBytes);
-            if (elect_one()) {
-#pragma unroll
-              for (int k16 = 0; k16 < 8; ++k16)
-                umma_f16_ts(tmem_base + 384u + (uint32_t)t * 64u, tmem_base + 256u + (uint32_t)t * 64u + (uint32_t)k16 * 8u,
-                            make_desc_mn_sw128(aV + (uint32_t)k16 * 2048u, kAtomBytes), idesc_o, (j | k16) != 0);
-              umma_commit(&bar_pv[t]);
-              if (npv[t ^ 1] > j) umma_commit(&empty_v[st]);  // both tiles have consumed this V stage
-            }
-            __syncwarp();
-            npv[t] = j + 1;
-            progressed = true;
+    } else {                                  // A/B: the interleaved order S_0, PV_0, S_1, PV_1
+      for (int j = 0; j < ntiles; ++j) {
+        for (int t = 0; t < 2; ++t) {
+          if (j + 1 < ntiles) {
+            mbar_wait(&bar_sfree[t], (uint32_t)j & 1u);
+            issue_s(t, j + 1);
           }
+          issue_pv(t, j);
         }
       }
-      if (progressed) spins = 0;
-      else if (++spins > (1u << 26)) __trap();      // a protocol bug must not hang the GPU box
     }
   } else {
     // ---- softmax warpgroup t: one thread per query row of tile t
@@ -842,14 +844,13 @@ attention_pp_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_consta
                    a_bar_pv = smem_u32(&bar_pv[t]);
     float m = -INFINITY, l = 0.f;
     const float sl2 = p.scale_log2;
-    // The warp of tile 0 and the warp of tile 1 with the same lane quarter share one SM sub-partition and its SFU. Left
-    // alone they drift into the exponential phase together, halve each other's SFU rate and then both sit in their
-    // load / max / store phases with the SFU idle (measured: 1313 clk per tile against a 768 clk SFU bound). A token
-    // passed through two named barriers per quarter makes the exponential phases ALTERNATE: while one warp owns the SFU
-    // the other does its tcgen05.ld, row max, rescale and P stores -- the ordering FlashAttention-4 imposes between its
-    // two softmax warpgroups. Tile 1 hands the first token to tile 0.
+    // Optional (p.pp_alternate, off by default): a token passed through two named barriers per lane quarter makes the
+    // exponential phases of the tile-0 and tile-1 warps that share an SM sub-partition (and its SFU) ALTERNATE, the ordering
+    // FlashAttention-4 imposes between its softmax warpgroups. Measured: no effect with MMA order 1 (2.887 vs 2.884 ms),
+    // needed with order 0 (2.95 vs 3.39 ms). Kept for A/B runs.
     const int bar_mine = 1 + qd * 2 + t, bar_other = 1 + qd * 2 + (t ^ 1);
-    if (t == 1) named_bar_arrive(bar_other, 64);
+    const bool alternate = p.pp_alternate != 0;
+    if (alternate && t == 1) named_bar_arrive(bar_other, 64);
     for (int j = 0; j < ntiles; ++j) {
       const int valid = j < t0 ? min(128, p.nk[0] - j * 128) : min(128, p.nk[1] - (j - t0) * 128);
       mbar_wait_a(a_bar_s, (uint32_t)j & 1u);
@@ -908,7 +909,7 @@ attention_pp_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_consta
       }
       const F2 sl2x2 = f2_make(sl2, sl2), nmx2 = f2_make(-m, -m);
       float ls0 = 0.f, ls1 = 0.f;
-      named_bar_sync(bar_mine, 64);                     // my turn on the SFU
+      if (alternate) named_bar_sync(bar_mine, 64);      // my turn on the SFU
 #pragma unroll
       for (int c = 0; c < 4; ++c) {                     // 4 chunks of 16 column pairs = one 16-register TMEM store each
         uint32_t pk[16];
@@ -933,14 +934,14 @@ attention_pp_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_consta
         }
         tmem_st16(tP + c * 16, pk);
       }
-      named_bar_arrive(bar_other, 64);                  // the other tile's warp may start its exponentials
+      if (alternate) named_bar_arrive(bar_other, 64);   // the other tile's warp may start its exponentials
       if (!kSumInV) l = l * alpha + (ls0 + ls1);
       tmem_st_wait();
       tc_fence_before();
       __syncwarp();
       if (lane == 0) mbar_arrive_a(a_bar_p);
     }
-    if (t == 0) named_bar_sync(bar_mine, 64);           // consume the last token so that no arrival is left pending
+    if (alternate && t == 0) named_bar_sync(bar_mine, 64);   // consume the last token so that no arrival is left pending
     // ---- epilogue: O_t row / row sum -> global
     mbar_wait_a(a_bar_pv, (uint32_t)(ntiles - 1) & 1u);
     tc_fence_after();
@@ -1092,6 +1093,10 @@ cudaError_t launch_attention(cudaStream_t stream, const AttnArgs& a, const char*
       if (e != cudaSuccess) { *err = "cudaFuncSetAttribute(attention_pp_kernel)"; return e; }
       pp_set_dev[cur_dev & 63] = true;
     }
+    static const int pp_alt_env = getenv("MVB_PP_ALT") ? atoi(getenv("MVB_PP_ALT")) : 0;
+    p.pp_alternate = pp_alt_env;
+    static const int pp_order_env = getenv("MVB_PP_ORDER") ? atoi(getenv("MVB_PP_ORDER")) : 1;
+    p.pp_order = pp_order_env;
     dim3 grid_pp((a.Nq + 255) / 256, a.heads, a.NF);
     pp_kernels[p.sum_in_v ? 1 : 0][pp_idx]<<<grid_pp, 320, smem_pp, stream>>>(tq, tk0, tv0, tk1, tv1, p);
     cudaError_t e = cudaGetLastError();

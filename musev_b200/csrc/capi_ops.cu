@@ -93,6 +93,19 @@ int mvb_op_groupnorm(const void* x0, int c0, const void* x1, int c1, int NF, int
   return MVB_OK;
 }
 
+int mvb_op_groupnorm_fused(const void* x0, int c0, const void* x1, int c1, int NF, int HW, int groups, int frames_per_stat,
+                           float eps, const float* gamma, const float* beta, int silu, void* y, float* scratch,
+                           unsigned int* barrier_word, unsigned int* arrivals, void* stream) {
+  if (!barrier_word || !arrivals) return fail("mvb_op_groupnorm_fused: null barrier word", cudaSuccess);
+  int dev = 0, sms = 148;
+  cudaGetDevice(&dev);
+  cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+  cudaError_t e = gn_fused((cudaStream_t)stream, (const __half*)x0, c0, (const __half*)x1, c1, NF, HW, groups, scratch,
+                           frames_per_stat, eps, gamma, beta, silu, (__half*)y, sms, barrier_word, arrivals);
+  if (e != cudaSuccess) return fail("mvb_op_groupnorm_fused", e == cudaErrorInvalidValue ? cudaSuccess : e);
+  return MVB_OK;
+}
+
 int mvb_op_layernorm(const void* x, long long M, int C, float eps, const float* gamma, const float* beta, void* y,
                      void* stream) {
   cudaError_t e = layernorm((cudaStream_t)stream, (const __half*)x, M, C, eps, gamma, beta, (__half*)y);

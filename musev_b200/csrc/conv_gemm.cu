@@ -32,8 +32,9 @@ static constexpr int kStageBytes = kABytes + kBBytes;
 static constexpr int kStagingBufBytes = 128 * 64;               // 128 rows x 32 fp16 output columns
 static constexpr int kStagingDepth = 4;                         // staging buffers per column half (3 TMA stores in flight)
 static constexpr int kStagingBytes = 2 * kStagingDepth * kStagingBufBytes;
-static constexpr int kRingBytes = 160 * 1024;                 // operand ring, split into nstages stages
-static constexpr int kSmemBytes = kRingBytes + kStagingBytes + 1024 /*align*/ + 256 /*barriers*/;
+static constexpr int kRingBytes = 156 * 1024;                 // operand ring, split into nstages stages
+static constexpr int kBiasBytes = 8 * 128 * 4;                // per epilogue warp: the bias of its (up to) 128 accumulator columns of a tile
+static constexpr int kSmemBytes = kRingBytes + kStagingBytes + kBiasBytes + 1024 /*align*/ + 256 /*barriers*/;
 
 __device__ __forceinline__ float gelu_erf(float x) { return 0.5f * x * (1.f + erff(x * 0.70710678118654752440f)); }
 __device__ __forceinline__ float silu(float x) { return __fdividef(x, 1.f + __expf(-x)); }
@@ -109,7 +110,8 @@ conv_gemm_kernel(const __grid_constant__ AMaps tmA, const __grid_constant__ CUte
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
   uint8_t* staging = smem + kRingBytes;
-  uint64_t* bars = reinterpret_cast<uint64_t*>(staging + kStagingBytes);
+  float* sbias = reinterpret_cast<float*>(staging + kStagingBytes);      // [8 epilogue warps][128]
+  uint64_t* bars = reinterpret_cast<uint64_t*>(staging + kStagingBytes + kBiasBytes);
   uint64_t* full = bars;                       // [kMaxStages]
   uint64_t* empty = bars + kMaxStages;         // [kMaxStages]
   uint64_t* tfull = bars + 2 * kMaxStages;     // [2]
@@ -282,6 +284,22 @@ conv_gemm_kernel(const __grid_constant__ AMaps tmA, const __grid_constant__ CUte
         }
       };
       load_res(half * acc_step, rcur);
+      // Bias of this warp's accumulator columns of the tile -> its private smem slice, issued BEFORE the accumulator wait so
+      // that the global-load latency hides behind the mainloop. (ncu on the level-0 N = K = 320 + residual GEMM: 20 % of
+      // all samples were long-scoreboard stalls on the per-chunk bias LDGs, which every thread issued and consumed at once.)
+      float* wbias = sbias + (warp - 4) * 128;
+      if constexpr (kEpi != kEpiGeneric) {
+        __syncwarp();                                   // the previous tile's reads of this slice are done
+#pragma unroll
+        for (int k = 0; k < 128 / 32; ++k) {
+          const int cw = k * 32 + lane;                 // position inside this warp's column list
+          const int cc = half * acc_step + (cw / acc_step) * 2 * acc_step + (cw % acc_step);   // accumulator column in the tile
+          float bv = 0.f;
+          if (p.bias && cc < p.block_n && ncol0 + cc < p.N) bv = __ldg(p.bias + ncol0 + cc);
+          wbias[cw] = bv;
+        }
+        __syncwarp();
+      }
 
       mbar_wait(&tfull[as], aphase);
       tc_fence_after();
@@ -297,6 +315,7 @@ conv_gemm_kernel(const __grid_constant__ AMaps tmA, const __grid_constant__ CUte
           if (nbase < p.N) {     // uniform per column half: the skipped chunks skip their barrier as a group
             uint8_t* buf = staging + (half * kStagingDepth + (chunk_iter % kStagingDepth)) * kStagingBufBytes;
             const F2 alpha2 = f2_make(p.alpha, p.alpha);
+            const float* cbias = wbias + ((c0 - half * acc_step) / (2 * acc_step)) * acc_step;   // this chunk's staged bias
 #pragma unroll
             for (int g = 0; g < 4; ++g) {      // 8 output columns = one 16-byte staging store
               uint32_t o[4];
@@ -308,11 +327,9 @@ conv_gemm_kernel(const __grid_constant__ AMaps tmA, const __grid_constant__ CUte
 #pragma unroll
                 for (int e = 0; e < 4; ++e) {
                   const int j = j0 + 2 * e;
-                  float2 bv = make_float2(0.f, 0.f), bg = make_float2(0.f, 0.f);
-                  if (p.bias) {
-                    bv = __ldg(reinterpret_cast<const float2*>(p.bias + nb + j));
-                    bg = __ldg(reinterpret_cast<const float2*>(p.bias + nb + 16 + j));
-                  }
+                  // staged bias: this chunk's 64 accumulator columns start at cbias; block g/2 holds [16 value | 16 gate]
+                  const float2 bv = *reinterpret_cast<const float2*>(cbias + (g >> 1) * 32 + j);
+                  const float2 bg = *reinterpret_cast<const float2*>(cbias + (g >> 1) * 32 + 16 + j);
                   const F2 val = f2_add(f2_make(__uint_as_float(vv[j]), __uint_as_float(vv[j + 1])), f2_make(bv.x, bv.y));
                   const F2 gat = f2_add(f2_make(__uint_as_float(vv[16 + j]), __uint_as_float(vv[16 + j + 1])),
                                         f2_make(bg.x, bg.y));
@@ -322,11 +339,8 @@ conv_gemm_kernel(const __grid_constant__ AMaps tmA, const __grid_constant__ CUte
                   o[e] = *reinterpret_cast<const uint32_t*>(&h2);
                 }
               } else {
-                float4 b0 = make_float4(0.f, 0.f, 0.f, 0.f), b1 = b0;
-                if (p.bias) {
-                  b0 = __ldg(reinterpret_cast<const float4*>(p.bias + nbase) + 2 * g);
-                  b1 = __ldg(reinterpret_cast<const float4*>(p.bias + nbase) + 2 * g + 1);
-                }
+                float4 b0 = *reinterpret_cast<const float4*>(cbias + 8 * g);
+                float4 b1 = *reinterpret_cast<const float4*>(cbias + 8 * g + 4);
                 if (radd) {
                   const float4 a0 = __ldg(reinterpret_cast<const float4*>(radd + nbase) + 2 * g);
                   const float4 a1 = __ldg(reinterpret_cast<const float4*>(radd + nbase) + 2 * g + 1);

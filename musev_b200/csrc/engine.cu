@@ -4,6 +4,7 @@
 
 #include <math.h>
 #include <stdio.h>
+#include <stdlib.h>
 #include <string.h>
 
 #include "attention.cuh"
@@ -140,12 +141,16 @@ Engine::Engine(const mvb_config& cfg, int device, int kind) : cfg_(cfg), device_
       cudaFree(dd);    // synchronises with the kernel
     } else err_ = "cudaMalloc(ones descriptors) failed";
   }
+  cudaMalloc(&gn_counter_dev_, sizeof(unsigned int));
+  cudaMemset(gn_counter_dev_, 0, sizeof(unsigned int));
+  gn_fused_ = !(getenv("MVB_GN_FUSED") && atoi(getenv("MVB_GN_FUSED")) == 0);
   cudaMalloc(&zero_idx_dev_, 64 * sizeof(int));
   cudaMalloc(&fidx_dev_, 128 * sizeof(float));
 }
 
 Engine::~Engine() {
   if (slab_) cudaFree(slab_);
+  if (gn_counter_dev_) cudaFree(gn_counter_dev_);
   if (zero_idx_dev_) cudaFree(zero_idx_dev_);
   if (fidx_dev_) cudaFree(fidx_dev_);
 }
@@ -685,6 +690,12 @@ struct Engine::Fwd {
   void gn(const __half* x0, int C0, const __half* x1, int C1, int HW, int fps, float eps, const Norm& n, int silu,
           __half* y) {
     if (!ok || dry) return;
+    if (E->gn_fused_) {
+      cudaError_t e = gn_fused(s, x0, C0, x1, C1, NF, HW, E->cfg_.norm_num_groups, gn_part, fps, eps, n.g, n.b, silu, y,
+                               E->num_sms_, E->gn_counter_dev_, &E->gn_base_);
+      if (e != cudaSuccess) fail("groupnorm (fused)", e);
+      return;
+    }
     int chunks = 0;
     cudaError_t e = gn_stats(s, x0, C0, x1, C1, NF, HW, E->cfg_.norm_num_groups, gn_part, &chunks);
     if (e == cudaSuccess)

@@ -35,22 +35,17 @@ __device__ __forceinline__ void st_half8(__half* p, const Half8& v) {
 // grid (chunks, NF); block 256. Thread owns a fixed 8-channel vector column and strides over pixels, so its
 // accumulators stay in registers; groups are even-sized, so a half2 never straddles two groups. The block reduction is
 // deterministic (no atomics): per-(row slot, channel pair) partials go to smem and thread g sums group g in fixed order.
-__global__ void __launch_bounds__(256)
-gn_stats_kernel(const __half* __restrict__ x0, int C0, const __half* __restrict__ x1, int C1, int HW, int G,
-                float* __restrict__ part) {
-  extern __shared__ float2 spair[];  // [rows_per_iter][C/2] (sum, sumsq) per channel pair
+__device__ __forceinline__ void gn_stats_unit(const __half* __restrict__ x0, int C0, const __half* __restrict__ x1, int C1, int HW,
+                                              int G, float* __restrict__ part, int f, int chunk, int chunks, float2* spair) {
   const int C = C0 + C1;
   const int vecs = C / 8;
   const int pairs = C / 2;
   const int cpg2 = (C / G) / 2;      // channel pairs per group
-  // frames in reverse order: the tail of the tensor is what the producing GEMM wrote last and is still in L2
-  const int f = gridDim.y - 1 - blockIdx.y;
-  const int chunks = gridDim.x;
   const int cols_per_pass = vecs < (int)blockDim.x ? vecs : (int)blockDim.x;
   const int rows_per_iter = blockDim.x / cols_per_pass;
   const int r0 = threadIdx.x / cols_per_pass;
-  const int p_begin = (int)(((long long)HW * blockIdx.x) / chunks);
-  const int p_end = (int)(((long long)HW * (blockIdx.x + 1)) / chunks);
+  const int p_begin = (int)(((long long)HW * chunk) / chunks);
+  const int p_end = (int)(((long long)HW * (chunk + 1)) / chunks);
   for (int v0 = 0; v0 < vecs; v0 += cols_per_pass) {
     const int v = v0 + threadIdx.x % cols_per_pass;
     if (r0 < rows_per_iter && v < vecs) {
@@ -95,10 +90,18 @@ gn_stats_kernel(const __half* __restrict__ x0, int C0, const __half* __restrict_
         s += t.x;
         q += t.y;
       }
-    float* dst = part + ((size_t)f * chunks + blockIdx.x) * 2 * G + 2 * g;
+    float* dst = part + ((size_t)f * chunks + chunk) * 2 * G + 2 * g;
     dst[0] = s;
     dst[1] = q;
   }
+}
+
+__global__ void __launch_bounds__(256)
+gn_stats_kernel(const __half* __restrict__ x0, int C0, const __half* __restrict__ x1, int C1, int HW, int G,
+                float* __restrict__ part) {
+  extern __shared__ float2 spair[];  // [rows_per_iter][C/2] (sum, sumsq) per channel pair
+  // frames in reverse order: the tail of the tensor is what the producing GEMM wrote last and is still in L2
+  gn_stats_unit(x0, C0, x1, C1, HW, G, part, gridDim.y - 1 - blockIdx.y, blockIdx.x, gridDim.x, spair);
 }
 
 cudaError_t gn_stats(cudaStream_t s, const __half* x0, int C0, const __half* x1, int C1, int NF, int HW, int G,
@@ -124,9 +127,8 @@ cudaError_t gn_stats(cudaStream_t s, const __half* x0, int C0, const __half* x1,
 // Reduces the per-frame partials of one statistics group (fps consecutive frames) to mean / rstd per group:
 // stats[NF/fps][G][2]. grid (NF/fps, G), one warp per (statistics group, channel group): lanes walk the partials in a
 // fixed interleaved order, then a fixed shuffle tree -- deterministic.
-__global__ void gn_finalize_kernel(const float* __restrict__ part, int chunks, int fps, int G, float count, float eps,
-                                   float* __restrict__ stats) {
-  const int sg = blockIdx.x, g = blockIdx.y, lane = threadIdx.x;
+__device__ __forceinline__ void gn_finalize_unit(const float* __restrict__ part, int chunks, int fps, int G, float count, float eps,
+                                                 float* __restrict__ stats, int sg, int g, int lane) {
   float s = 0.f, q = 0.f;
   for (int i = lane; i < fps * chunks; i += 32) {
     const float2 pp = *reinterpret_cast<const float2*>(part + ((size_t)sg * fps * chunks + i) * 2 * G + 2 * g);
@@ -146,23 +148,25 @@ __global__ void gn_finalize_kernel(const float* __restrict__ part, int chunks, i
     stats[((size_t)sg * G + g) * 2 + 1] = rsqrtf(var + eps);
   }
 }
+__global__ void gn_finalize_kernel(const float* __restrict__ part, int chunks, int fps, int G, float count, float eps,
+                                   float* __restrict__ stats) {
+  gn_finalize_unit(part, chunks, fps, G, count, eps, stats, blockIdx.x, blockIdx.y, threadIdx.x);
+}
 
 // grid (pixel blocks, NF); block 256; each block streams ~64 KB.
-__global__ void __launch_bounds__(256)
-gn_apply_kernel(const __half* __restrict__ x0, int C0, const __half* __restrict__ x1, int C1, int HW, int G,
-                const float* __restrict__ stats, int fps, const float* __restrict__ gamma,
-                const float* __restrict__ beta, int silu, __half* __restrict__ y, int pix_per_block) {
-  extern __shared__ float sm_gn[];  // mean[G], rstd[G]
+__device__ __forceinline__ void gn_apply_unit(const __half* __restrict__ x0, int C0, const __half* __restrict__ x1, int C1, int HW,
+                                              int G, const float* __restrict__ stats, int fps, const float* __restrict__ gamma,
+                                              const float* __restrict__ beta, int silu, __half* __restrict__ y, int pix_per_block,
+                                              int f, int pblock, float* sm_gn) {
   const int C = C0 + C1;
   const int cpg = C / G;
-  const int f = blockIdx.y;
   for (int g = threadIdx.x; g < G; g += blockDim.x) {
     sm_gn[g] = stats[((size_t)(f / fps) * G + g) * 2];
     sm_gn[G + g] = stats[((size_t)(f / fps) * G + g) * 2 + 1];
   }
   __syncthreads();
   const int vecs = C / 8;
-  const int p0 = blockIdx.x * pix_per_block;
+  const int p0 = pblock * pix_per_block;
   const int p1 = min(HW, p0 + pix_per_block);
   const int total = (p1 - p0) * vecs;
   // a thread keeps the same channel vector when blockDim is a multiple of vecs; the affine terms are then loaded once
@@ -235,6 +239,67 @@ gn_apply_kernel(const __half* __restrict__ x0, int C0, const __half* __restrict_
   }
 }
 
+__global__ void __launch_bounds__(256)
+gn_apply_kernel(const __half* __restrict__ x0, int C0, const __half* __restrict__ x1, int C1, int HW, int G,
+                const float* __restrict__ stats, int fps, const float* __restrict__ gamma,
+                const float* __restrict__ beta, int silu, __half* __restrict__ y, int pix_per_block) {
+  extern __shared__ float sm_gn[];  // mean[G], rstd[G]
+  gn_apply_unit(x0, C0, x1, C1, HW, G, stats, fps, gamma, beta, silu, y, pix_per_block, blockIdx.y, blockIdx.x, sm_gn);
+}
+
+// ---- the three passes in ONE persistent launch: statistics -> grid barrier -> finalize -> grid barrier -> apply.
+// All blocks are co-resident (grid = occupancy x SMs), so a software barrier on a global counter is safe. The apply phase
+// walks the frames in the opposite order of the statistics phase, i.e. it starts with the frames the statistics phase read
+// last, which are still in L2 (126 MB): up to ~2/3 of the second read of a level-0 tensor (89 MB) no longer goes to HBM, and
+// two launches per GroupNorm (332 per forward) disappear. Bit-identical to the three-kernel path (same partial layout, same
+// fixed-order reductions).
+__device__ __forceinline__ void gn_grid_barrier(unsigned int* counter, unsigned int target) {
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    __threadfence();
+    atomicAdd(counter, 1u);
+    unsigned int spins = 0;
+    for (;;) {
+      unsigned int v;
+      asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(counter) : "memory");
+      if ((int)(v - target) >= 0) break;          // wrap-safe
+      if (++spins > (1u << 27)) __trap();         // a protocol bug must not hang the GPU box
+      __nanosleep(40);
+    }
+    __threadfence();
+  }
+  __syncthreads();
+}
+
+__global__ void __launch_bounds__(256)
+gn_fused_kernel(const __half* __restrict__ x0, int C0, const __half* __restrict__ x1, int C1, int NF, int HW, int G, int chunks,
+                float* __restrict__ part, float* __restrict__ stats, int fps, float count, float eps,
+                const float* __restrict__ gamma, const float* __restrict__ beta, int silu, __half* __restrict__ y,
+                int pix_per_block, int pblocks, unsigned int* counter, unsigned int base) {
+  extern __shared__ float2 sm_fused[];
+  // phase 1: per-(frame, chunk) partial sums, frames in reverse order (the producer's tail is still in L2)
+  for (int u = blockIdx.x; u < NF * chunks; u += gridDim.x) {
+    gn_stats_unit(x0, C0, x1, C1, HW, G, part, NF - 1 - u / chunks, u % chunks, chunks, sm_fused);
+    __syncthreads();                              // the smem tile is reused by the next unit
+  }
+  gn_grid_barrier(counter, base + gridDim.x);
+  // phase 2: one warp per (statistics group, channel group)
+  {
+    const int wpb = blockDim.x >> 5, warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int units = (NF / fps) * G;
+    if (warp < wpb)
+      for (int u = blockIdx.x * wpb + warp; u < units; u += gridDim.x * wpb)
+        gn_finalize_unit(part, chunks, fps, G, count, eps, stats, u / G, u % G, lane);
+  }
+  gn_grid_barrier(counter, base + 2u * gridDim.x);
+  // phase 3: apply, frames ascending (phase 1 finished on frame 0)
+  for (int u = blockIdx.x; u < NF * pblocks; u += gridDim.x) {
+    gn_apply_unit(x0, C0, x1, C1, HW, G, stats, fps, gamma, beta, silu, y, pix_per_block, u / pblocks, u % pblocks,
+                  reinterpret_cast<float*>(sm_fused));
+    __syncthreads();
+  }
+}
+
 cudaError_t gn_apply(cudaStream_t s, const __half* x0, int C0, const __half* x1, int C1, int NF, int HW, int G,
                      const float* part, int chunks, int fps, float eps, const float* gamma, const float* beta, int silu,
                      __half* y) {
@@ -260,6 +325,50 @@ cudaError_t gn_apply(cudaStream_t s, const __half* x0, int C0, const __half* x1,
   int blocks = (HW + ppb - 1) / ppb;
   gn_apply_kernel<<<dim3(blocks, NF), threads, 2 * G * sizeof(float), s>>>(x0, C0, x1, C1, HW, G, stats, fps, gamma, beta,
                                                                            silu, y, ppb);
+  return cudaGetLastError();
+}
+
+// One-launch GroupNorm (statistics + finalize + apply behind two grid barriers). `counter` is a zero-initialised device word
+// owned by the caller, `*base` the number of arrivals it has seen so far (host bookkeeping; launches must be stream-ordered).
+cudaError_t gn_fused(cudaStream_t s, const __half* x0, int C0, const __half* x1, int C1, int NF, int HW, int G, float* part,
+                     int fps, float eps, const float* gamma, const float* beta, int silu, __half* y, int num_sms,
+                     unsigned int* counter, unsigned int* base) {
+  ProfScope prof(s, KC_GROUPNORM);
+  if (!x1) C1 = 0;
+  const int C = C0 + C1;
+  if ((C0 % 8) || (C1 % 8) || (C % G) || ((C / G) % 2) || fps < 1 || (NF % fps) || G > 64) return cudaErrorInvalidValue;
+  // same work decomposition as gn_stats / gn_apply
+  int chunks = (8 * 148) / NF;
+  const int maxc = HW / 32 > 0 ? HW / 32 : 1;
+  if (chunks > maxc) chunks = maxc;
+  if (chunks > kGnMaxChunks) chunks = kGnMaxChunks;
+  if (chunks < 1) chunks = 1;
+  const int vecs = C / 8;
+  int threads = 256;
+  if (vecs <= 256 && (256 % vecs) != 0) threads = (256 / vecs) * vecs;
+  if (threads < 64) threads = 256;
+  const int cols = vecs < threads ? vecs : threads;
+  const int rows_per_pass = threads / cols > 0 ? threads / cols : 1;
+  int ppb = (int)(((long long)HW * NF + 148 * 24 - 1) / (148 * 24));
+  if (ppb < 4 * rows_per_pass) ppb = 4 * rows_per_pass;
+  if (ppb > HW) ppb = HW;
+  const int pblocks = (HW + ppb - 1) / ppb;
+  size_t smem = (size_t)(threads / cols) * (C / 2) * sizeof(float2);
+  if (smem < 2 * G * sizeof(float)) smem = 2 * G * sizeof(float);
+  int per_sm = 0;
+  cudaError_t e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, gn_fused_kernel, threads, smem);
+  if (e != cudaSuccess) return e;
+  if (per_sm < 1) return cudaErrorInvalidValue;
+  if (per_sm > 8) per_sm = 8;
+  long long units = (long long)NF * chunks;
+  if ((long long)NF * pblocks > units) units = (long long)NF * pblocks;
+  long long grid = (long long)per_sm * num_sms;      // every block must be resident: the kernel spins on a grid barrier
+  if (grid > units) grid = units;
+  float* stats = part + (size_t)NF * kGnMaxChunks * G * 2;
+  const float count = (float)fps * HW * (C / G);
+  gn_fused_kernel<<<(unsigned)grid, threads, smem, s>>>(x0, C0, x1, C1, NF, HW, G, chunks, part, stats, fps, count, eps, gamma, beta,
+                                                       silu, y, ppb, pblocks, counter, *base);
+  *base += 2u * (unsigned)grid;
   return cudaGetLastError();
 }
 

@@ -41,6 +41,12 @@ cudaError_t sinusoid(cudaStream_t s, const float* values, int n, int dim, __half
 cudaError_t expand_rows(cudaStream_t s, const __half* src, int B, int T, int D, const int* zero_t, int nzero, int act,
                         __half* out);
 cudaError_t silu_copy(cudaStream_t s, const __half* x, long long n, __half* y);
+// GroupNorm as ONE persistent launch (statistics -> grid barrier -> finalize -> grid barrier -> apply); same arithmetic and
+// scratch layout as gn_stats + gn_apply. `counter`: zero-initialised device word owned by the caller; `*base`: host count of
+// the arrivals it has seen (launches on one stream).
+cudaError_t gn_fused(cudaStream_t s, const __half* x0, int C0, const __half* x1, int C1, int NF, int HW, int G, float* part,
+                     int fps, float eps, const float* gamma, const float* beta, int silu, __half* y, int num_sms,
+                     unsigned int* counter, unsigned int* base);
 // VAE decoder helpers: post_quant 1x1 conv on the latent channels, in-place row softmax, output layout change with the
 // image post-processing affine + clamp
 cudaError_t latent_pointwise(cudaStream_t s, const void* x, int is_f32, int N, int C, int HW, const float* w, const float* b,

@@ -111,14 +111,26 @@ def temporal_attention(qkv, B, T, HW, heads, d, dp, scale):
     return out
 
 
-def groupnorm(x0, gamma, beta, groups=32, frames_per_stat=1, eps=1e-5, silu=False, x1=None):
-    """x0 [NF, HW, C0] fp16 (+ x1 [NF, HW, C1]); gamma/beta fp32 [C0+C1]."""
+_gn_barrier = {}     # device -> (zeroed uint32 tensor, ctypes arrival counter) of the one-launch GroupNorm
+
+
+def groupnorm(x0, gamma, beta, groups=32, frames_per_stat=1, eps=1e-5, silu=False, x1=None, fused=False):
+    """x0 [NF, HW, C0] fp16 (+ x1 [NF, HW, C1]); gamma/beta fp32 [C0+C1]. fused=True: the one-launch kernel the engine uses."""
     assert x0.dtype == torch.float16 and x0.is_contiguous() and (x1 is None or (x1.dtype == torch.float16 and x1.is_contiguous()))
     assert gamma.dtype == torch.float32 and beta.dtype == torch.float32
     NF, HW, C0 = x0.shape
     C1 = 0 if x1 is None else x1.shape[2]
     y = torch.empty((NF, HW, C0 + C1), dtype=torch.float16, device=x0.device)
     scratch = torch.empty(NF * 65 * groups * 2, dtype=torch.float32, device=x0.device)
+    if fused:
+        key = x0.device.index or 0
+        if key not in _gn_barrier:
+            _gn_barrier[key] = (torch.zeros(1, dtype=torch.int32, device=x0.device), C.c_uint(0))
+        word, arrivals = _gn_barrier[key]
+        _capi.check(_capi.lib().mvb_op_groupnorm_fused(x0.data_ptr(), C0, _ptr(x1), C1, NF, HW, groups, frames_per_stat, eps,
+                                                       gamma.data_ptr(), beta.data_ptr(), int(silu), y.data_ptr(),
+                                                       scratch.data_ptr(), word.data_ptr(), C.byref(arrivals), _stream()))
+        return y
     _capi.check(_capi.lib().mvb_op_groupnorm(x0.data_ptr(), C0, _ptr(x1), C1, NF, HW, groups, frames_per_stat, eps,
                                              gamma.data_ptr(), beta.data_ptr(), int(silu), y.data_ptr(),
                                              scratch.data_ptr(), _stream()))

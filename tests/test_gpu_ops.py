@@ -101,14 +101,18 @@ def test_geglu_and_fp32_out(ops):
 
 
 @pytest.mark.parametrize("NF,HW,C0,C1,fps,silu", [(4, 256, 320, 0, 1, True), (6, 64, 1280, 1280, 1, True),
-                                                  (6, 1024, 640, 320, 3, False), (4, 64, 64, 0, 2, True)])
-def test_groupnorm(ops, NF, HW, C0, C1, fps, silu):
+                                                  (6, 1024, 640, 320, 3, False), (4, 64, 64, 0, 2, True),
+                                                  (34, 4096, 320, 0, 17, True), (34, 4096, 320, 0, 1, False)])
+@pytest.mark.parametrize("fused", [False, True])
+def test_groupnorm(ops, NF, HW, C0, C1, fps, silu, fused):
     torch.manual_seed(5)
     x0 = (torch.randn(NF, HW, C0, device=dev) * 2 + 0.5).half()
     x1 = (torch.randn(NF, HW, C1, device=dev) - 1).half() if C1 else None
     C = C0 + C1
     g, b = torch.randn(C, device=dev), torch.randn(C, device=dev)
-    y = ops.groupnorm(x0, g, b, 32, fps, 1e-5, silu, x1)
+    y = ops.groupnorm(x0, g, b, 32, fps, 1e-5, silu, x1, fused=fused)
+    if fused:      # one launch vs three launches: same partial layout and reduction order -> bit-identical
+        assert torch.equal(y, ops.groupnorm(x0, g, b, 32, fps, 1e-5, silu, x1)) and torch.equal(y, ops.groupnorm(x0, g, b, 32, fps, 1e-5, silu, x1, fused=True))
     x = x0 if x1 is None else torch.cat([x0, x1], 2)
     ref = F.group_norm(x.float().view(NF // fps, fps * HW, C).permute(0, 2, 1), 32, g, b, 1e-5)
     if silu:

@@ -268,3 +268,29 @@ def test_parallel_denoise_loop_euler_and_eta(built_lib):
     c = den(lat1.to(dev), cond.to(dev), prompt.to(dev), num_inference_steps=2, guidance_scale=3.5, context_frames=8,
             context_overlap=4).latents
     assert torch.equal(a, b) and torch.isfinite(a).all() and (a - c).abs().max().item() > 1e-2
+
+
+@pytest.mark.parametrize("preset,frames,h,w", [("musev_referencenet", 12, 64, 64), ("musev", 8, 64, 96), ("musev_referencenet", 16, 64, 64)])
+def test_full_width_other_window_shapes_vs_fp32_oracle(built_lib, preset, frames, h, w):
+    """Full-width forward at the other shapes the BASELINE configs produce: the short last windows of configs 3 / 4
+    (T = 12+1, 8+1), 512x768 (64x96 latents, config 5) and the heavier `musev_referencenet` preset at the
+    config-2 shape -- against the fp32 oracle on the same fp16-rounded weights (same bound as the small-shape forward test)."""
+    from musev_b200.unet import UNet3DConditionModel
+    from oracle.unet3d_oracle import UNet3DOracle
+    torch.backends.cudnn.allow_tf32 = False
+    torch.backends.cuda.matmul.allow_tf32 = False
+    cfg = preset_config(preset)
+    sd16 = make_state_dict(cfg, seed=0, dtype=torch.float16)
+    model = UNet3DConditionModel(cfg, device=dev, dtype=torch.float32)
+    model.load_state_dict(sd16)
+    oracle = UNet3DOracle(cfg, sd16, device=dev, dtype=torch.float32)
+    del sd16
+    inp = make_inputs(cfg, batch=2, frames=frames, h=h, w=w, n_vis_cond=1, seed=99)
+    kw = _call_kwargs(inp, 8, 1.0)
+    with torch.no_grad():
+        ref = oracle(inp["sample"], 451, inp["encoder_hidden_states"], **kw)
+        out = model(inp["sample"].to(dev), 451, inp["encoder_hidden_states"].to(dev),
+                    **{k: _to(v, dev, torch.float32) for k, v in kw.items()}).sample
+    err = (out - ref).abs().max().item()
+    _record(f"fwd_full_{preset}_T{frames + 1}_{h}x{w}_vs_oracle", err)
+    assert torch.isfinite(out).all() and err < 1.2e-2, err
