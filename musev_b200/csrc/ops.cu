@@ -35,6 +35,20 @@ __device__ __forceinline__ void st_half8(__half* p, const Half8& v) {
 // grid (chunks, NF); block 256. Thread owns a fixed 8-channel vector column and strides over pixels, so its
 // accumulators stay in registers; groups are even-sized, so a half2 never straddles two groups. The block reduction is
 // deterministic (no atomics): per-(row slot, channel pair) partials go to smem and thread g sums group g in fixed order.
+// Statistics are carried as (count, mean, M2 = sum of squared deviations) triples and merged with Chan's parallel update, never
+// as raw sum / sum-of-squares: E[x^2] - E[x]^2 in fp32 loses the variance once |mean| >> std (activations of real checkpoints
+// have such channels). Each thread accumulates deviations from a pilot value (its first sample), which
+// keeps the running sums at the scale of the spread, not of the mean.
+__device__ __forceinline__ void chan_merge(float& n, float& mean, float& m2, float nb, float mb, float m2b) {
+  if (nb <= 0.f) return;
+  const float nt = n + nb;
+  const float delta = mb - mean;
+  const float w = __fdividef(nb, nt);   // counts are small integers: the approximate reciprocal is exact enough (1 ulp)
+  mean = fmaf(delta, w, mean);
+  m2 = m2 + m2b + delta * delta * n * w;
+  n = nt;
+}
+
 __device__ __forceinline__ void gn_stats_unit(const __half* __restrict__ x0, int C0, const __half* __restrict__ x1, int C1, int HW,
                                               int G, float* __restrict__ part, int f, int chunk, int chunks, float2* spair) {
   const int C = C0 + C1;
@@ -53,8 +67,15 @@ __device__ __forceinline__ void gn_stats_unit(const __half* __restrict__ x0, int
       const __half* src = (c < C0) ? x0 + (size_t)f * HW * C0 + c : x1 + (size_t)f * HW * C1 + (c - C0);
       const int ld = (c < C0) ? C0 : C1;
       float s[4] = {0, 0, 0, 0}, q[4] = {0, 0, 0, 0};
+      __half2 piv2[4];
       int p = p_begin + r0;
-      // four independent 16-byte loads in flight per thread
+      {                                // pilot: the first sample of every channel pair (independent of the loads below)
+        const Half8 h0 = ld_half8(src + (size_t)(p < p_end ? p : p_begin) * ld);
+#pragma unroll
+        for (int j = 0; j < 4; ++j) piv2[j] = __low2half2(h0.h[j]);
+      }
+      // four independent 16-byte loads in flight per thread; the deviation from the pilot is taken in fp16 (one HSUB2 per
+      // pair: exact for neighbours of the pilot, 2^-11 relative otherwise), everything after it in fp32
       for (; p + 3 * rows_per_iter < p_end; p += 4 * rows_per_iter) {
         Half8 hv[4];
 #pragma unroll
@@ -63,7 +84,7 @@ __device__ __forceinline__ void gn_stats_unit(const __half* __restrict__ x0, int
         for (int u = 0; u < 4; ++u)
 #pragma unroll
           for (int j = 0; j < 4; ++j) {
-            const float2 t = __half22float2(hv[u].h[j]);
+            const float2 t = __half22float2(__hsub2(hv[u].h[j], piv2[j]));
             s[j] += t.x + t.y;
             q[j] = fmaf(t.x, t.x, fmaf(t.y, t.y, q[j]));
           }
@@ -72,31 +93,42 @@ __device__ __forceinline__ void gn_stats_unit(const __half* __restrict__ x0, int
         const Half8 hv = ld_half8(src + (size_t)p * ld);
 #pragma unroll
         for (int j = 0; j < 4; ++j) {
-          const float2 t = __half22float2(hv.h[j]);
+          const float2 t = __half22float2(__hsub2(hv.h[j], piv2[j]));
           s[j] += t.x + t.y;
           q[j] = fmaf(t.x, t.x, fmaf(t.y, t.y, q[j]));
         }
       }
+      float piv[4];
 #pragma unroll
-      for (int j = 0; j < 4; ++j) spair[(size_t)r0 * pairs + v * 4 + j] = make_float2(s[j], q[j]);
+      for (int j = 0; j < 4; ++j) piv[j] = __low2float(piv2[j]);
+      // (mean, M2) of this thread's 2 x count samples of each pair
+      const int span = p_end - p_begin - r0;
+      const float cnt = span > 0 ? 2.f * (float)((span + rows_per_iter - 1) / rows_per_iter) : 0.f;
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        const float ms = cnt > 0.f ? s[j] / cnt : 0.f;
+        spair[(size_t)r0 * pairs + v * 4 + j] = make_float2(piv[j] + ms, fmaxf(q[j] - s[j] * ms, 0.f));
+      }
     }
   }
   __syncthreads();
   for (int g = threadIdx.x; g < G; g += blockDim.x) {
-    float s = 0.f, q = 0.f;
-    for (int r = 0; r < rows_per_iter; ++r)
+    float n = 0.f, mean = 0.f, m2 = 0.f;
+    for (int r = 0; r < rows_per_iter; ++r) {
+      const int span = p_end - p_begin - r;
+      const float cnt = span > 0 ? 2.f * (float)((span + rows_per_iter - 1) / rows_per_iter) : 0.f;
       for (int pc = g * cpg2; pc < (g + 1) * cpg2; ++pc) {
         const float2 t = spair[(size_t)r * pairs + pc];
-        s += t.x;
-        q += t.y;
+        chan_merge(n, mean, m2, cnt, t.x, t.y);
       }
+    }
     float* dst = part + ((size_t)f * chunks + chunk) * 2 * G + 2 * g;
-    dst[0] = s;
-    dst[1] = q;
+    dst[0] = mean;                     // count is implied: (p_end - p_begin) * channels per group
+    dst[1] = m2;
   }
 }
 
-__global__ void __launch_bounds__(256)
+__global__ void __launch_bounds__(256, 8)     // 8 resident blocks per SM = 32 registers: the kernel is latency-bound
 gn_stats_kernel(const __half* __restrict__ x0, int C0, const __half* __restrict__ x1, int C1, int HW, int G,
                 float* __restrict__ part) {
   extern __shared__ float2 spair[];  // [rows_per_iter][C/2] (sum, sumsq) per channel pair
@@ -127,30 +159,31 @@ cudaError_t gn_stats(cudaStream_t s, const __half* x0, int C0, const __half* x1,
 // Reduces the per-frame partials of one statistics group (fps consecutive frames) to mean / rstd per group:
 // stats[NF/fps][G][2]. grid (NF/fps, G), one warp per (statistics group, channel group): lanes walk the partials in a
 // fixed interleaved order, then a fixed shuffle tree -- deterministic.
-__device__ __forceinline__ void gn_finalize_unit(const float* __restrict__ part, int chunks, int fps, int G, float count, float eps,
+__device__ __forceinline__ void gn_finalize_unit(const float* __restrict__ part, int chunks, int fps, int G, int HW, int cpg, float eps,
                                                  float* __restrict__ stats, int sg, int g, int lane) {
-  float s = 0.f, q = 0.f;
+  float n = 0.f, mean = 0.f, m2 = 0.f;
   for (int i = lane; i < fps * chunks; i += 32) {
+    const int chunk = i % chunks;
+    const int pix = (int)(((long long)HW * (chunk + 1)) / chunks) - (int)(((long long)HW * chunk) / chunks);
     const float2 pp = *reinterpret_cast<const float2*>(part + ((size_t)sg * fps * chunks + i) * 2 * G + 2 * g);
-    s += pp.x;
-    q += pp.y;
+    chan_merge(n, mean, m2, (float)pix * (float)cpg, pp.x, pp.y);
   }
 #pragma unroll
-  for (int o = 16; o > 0; o >>= 1) {
-    s += __shfl_xor_sync(0xffffffffu, s, o);
-    q += __shfl_xor_sync(0xffffffffu, q, o);
+  for (int o = 16; o > 0; o >>= 1) {   // fixed butterfly: deterministic
+    const float nb = __shfl_xor_sync(0xffffffffu, n, o);
+    const float mb = __shfl_xor_sync(0xffffffffu, mean, o);
+    const float qb = __shfl_xor_sync(0xffffffffu, m2, o);
+    chan_merge(n, mean, m2, nb, mb, qb);
   }
   if (lane == 0) {
-    const float mean = s / count;
-    float var = q / count - mean * mean;
-    var = var < 0.f ? 0.f : var;
+    const float var = n > 0.f ? fmaxf(m2 / n, 0.f) : 0.f;
     stats[((size_t)sg * G + g) * 2] = mean;
     stats[((size_t)sg * G + g) * 2 + 1] = rsqrtf(var + eps);
   }
 }
-__global__ void gn_finalize_kernel(const float* __restrict__ part, int chunks, int fps, int G, float count, float eps,
+__global__ void gn_finalize_kernel(const float* __restrict__ part, int chunks, int fps, int G, int HW, int cpg, float eps,
                                    float* __restrict__ stats) {
-  gn_finalize_unit(part, chunks, fps, G, count, eps, stats, blockIdx.x, blockIdx.y, threadIdx.x);
+  gn_finalize_unit(part, chunks, fps, G, HW, cpg, eps, stats, blockIdx.x, blockIdx.y, threadIdx.x);
 }
 
 // grid (pixel blocks, NF); block 256; each block streams ~64 KB.
@@ -273,7 +306,7 @@ __device__ __forceinline__ void gn_grid_barrier(unsigned int* counter, unsigned 
 
 __global__ void __launch_bounds__(256)
 gn_fused_kernel(const __half* __restrict__ x0, int C0, const __half* __restrict__ x1, int C1, int NF, int HW, int G, int chunks,
-                float* __restrict__ part, float* __restrict__ stats, int fps, float count, float eps,
+                float* __restrict__ part, float* __restrict__ stats, int fps, float eps,
                 const float* __restrict__ gamma, const float* __restrict__ beta, int silu, __half* __restrict__ y,
                 int pix_per_block, int pblocks, unsigned int* counter, unsigned int base) {
   extern __shared__ float2 sm_fused[];
@@ -289,7 +322,7 @@ gn_fused_kernel(const __half* __restrict__ x0, int C0, const __half* __restrict_
     const int units = (NF / fps) * G;
     if (warp < wpb)
       for (int u = blockIdx.x * wpb + warp; u < units; u += gridDim.x * wpb)
-        gn_finalize_unit(part, chunks, fps, G, count, eps, stats, u / G, u % G, lane);
+        gn_finalize_unit(part, chunks, fps, G, HW, (C0 + C1) / G, eps, stats, u / G, u % G, lane);
   }
   gn_grid_barrier(counter, base + 2u * gridDim.x);
   // phase 3: apply, frames ascending (phase 1 finished on frame 0)
@@ -309,8 +342,7 @@ cudaError_t gn_apply(cudaStream_t s, const __half* x0, int C0, const __half* x1,
   if (fps < 1 || (NF % fps) || G > 64) return cudaErrorInvalidValue;
   // mean / rstd live right behind the partial sums in the caller's scratch: NF*(kGnMaxChunks+1)*G*2 floats in total
   float* stats = const_cast<float*>(part) + (size_t)NF * kGnMaxChunks * G * 2;
-  const float count = (float)fps * HW * (C / G);
-  gn_finalize_kernel<<<dim3(NF / fps, G), 32, 0, s>>>(part, chunks, fps, G, count, eps, stats);
+  gn_finalize_kernel<<<dim3(NF / fps, G), 32, 0, s>>>(part, chunks, fps, G, HW, C / G, eps, stats);
   // ~64 KB of fp16 per block, block size a multiple of the number of channel vectors when possible
   const int vecs = C / 8;
   int threads = 256;
@@ -365,8 +397,7 @@ cudaError_t gn_fused(cudaStream_t s, const __half* x0, int C0, const __half* x1,
   long long grid = (long long)per_sm * num_sms;      // every block must be resident: the kernel spins on a grid barrier
   if (grid > units) grid = units;
   float* stats = part + (size_t)NF * kGnMaxChunks * G * 2;
-  const float count = (float)fps * HW * (C / G);
-  gn_fused_kernel<<<(unsigned)grid, threads, smem, s>>>(x0, C0, x1, C1, NF, HW, G, chunks, part, stats, fps, count, eps, gamma, beta,
+  gn_fused_kernel<<<(unsigned)grid, threads, smem, s>>>(x0, C0, x1, C1, NF, HW, G, chunks, part, stats, fps, eps, gamma, beta,
                                                        silu, y, ppb, pblocks, counter, *base);
   *base += 2u * (unsigned)grid;
   return cudaGetLastError();

@@ -269,3 +269,16 @@ def test_sampler_steps_match_oracle(ops):
         if noise is None:
             assert (a_t_prev.prev_sample.cpu() - po).abs().max().item() < 1e-4
         xs, xo = po.to(dev), po
+
+
+@pytest.mark.parametrize("fused", [False, True])
+def test_groupnorm_large_mean(ops, fused):
+    """|mean| >> std: sum / sum-of-squares statistics in fp32 lose the variance here (E[x^2] - E[x]^2 cancels to ~6 % at
+    mean 2048, std 4); the (count, mean, M2) statistics do not."""
+    torch.manual_seed(11)
+    NF, HW, C = 4, 1024, 320
+    x = (torch.randn(NF, HW, C, device=dev) * 4 + 2048).half()
+    g, b = torch.randn(C, device=dev), torch.randn(C, device=dev)
+    y = ops.groupnorm(x, g, b, 32, 1, 1e-5, False, None, fused=fused)
+    ref = F.group_norm(x.float().permute(0, 2, 1), 32, g, b, 1e-5).permute(0, 2, 1)
+    _close(y, ref, rel=2e-3, abs_=4e-3)
