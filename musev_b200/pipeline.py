@@ -86,8 +86,6 @@ class ParallelDenoiser:
         if cfg_split:
             if self.world % 2:
                 raise ValueError("cfg_split needs an even number of ranks")
-            if controlnet_fn is not None:
-                raise NotImplementedError("cfg_split with a ControlNet callback is not implemented")
             per_rank = assign_windows([len(c) for c in contexts], self.world // 2)
             mine = per_rank[self.rank // 2]
             half = self.rank % 2
@@ -153,7 +151,10 @@ class ParallelDenoiser:
                     model_in = torch.cat([cond2, torch.cat([lat_c] * 2)], dim=2)    # :1908-1946
                 kw = dict(unet_kwargs)
                 if controlnet_fn is not None:
-                    down_res, mid_res = controlnet_fn(c, model_in, t, i)            # :2022-2038
+                    if cfg_split:      # the callback gets this rank's half of the CFG batch and which rows it is
+                        down_res, mid_res = controlnet_fn(c, model_in, t, i, rows)
+                    else:
+                        down_res, mid_res = controlnet_fn(c, model_in, t, i)        # :2022-2038
                     kw["down_block_additional_residuals"] = down_res
                     kw["mid_block_additional_residual"] = mid_res
                 eps = self.unet(model_in, t, prompt_embeds[rows] if cfg_split else prompt_embeds, sample_index=sub_idx,
@@ -195,12 +196,18 @@ def make_controlnet_fn(controlnet, controlnet_latents: torch.Tensor, prompt_embe
     Returns residuals shaped `(b t) c h w` with b = 2B, which is what `UNet3DConditionModel.forward` takes."""
     vis = list(range(n_vision_cond))
 
-    def fn(c, latent_model_input, t, i=0):
+    def fn(c, latent_model_input, t, i=0, rows=None):
+        """rows: with `ParallelDenoiser(cfg_split=True)` the slice of the CFG batch this rank runs (`latent_model_input` then
+        holds only those rows); the prompt and condition latents are sliced to match."""
         ctx = vis + [ci + n_vision_cond for ci in c]                                       # :1997-2000
         idx = torch.tensor(ctx, dtype=torch.long, device=controlnet_latents.device)
         lat_c = controlnet_latents.index_select(2, idx)                                    # :2008-2010
         b2 = latent_model_input.shape[0]
-        if guess_mode:                                                                     # :1219-1225: cond half only
+        if rows is not None:
+            if guess_mode:
+                raise NotImplementedError("guess_mode runs the ControlNet on the conditional half only; not combined with cfg_split")
+            x, enc, lat_c = latent_model_input, prompt_embeds[rows], lat_c[rows]
+        elif guess_mode:                                                                   # :1219-1225: cond half only
             x = latent_model_input[b2 // 2:]
             enc = prompt_embeds[prompt_embeds.shape[0] // 2:]
         else:

@@ -84,7 +84,23 @@ class OracleOpsDouble:
         return (a_p ** 0.5 * x0 + (1 - a_p) ** 0.5 * e).to(latents.dtype)
 
 
-def _loop_worker(rank, world, port, preset, out_path, cfg_split=False):
+class _FakeControlNet:
+    """Deterministic stand-in with the diffusers ControlNetModel call signature: residual maps that depend on the sample,
+    the timestep, the prompt rows and the condition latents (so that a wrong row / frame slice changes the result)."""
+
+    def __init__(self, shapes):
+        self.shapes = shapes      # [(C, downscale)] of the 12 + 1 maps
+
+    def __call__(self, sample, t, enc, controlnet_cond_latents=None, conditioning_scale=1.0, guess_mode=False, return_dict=False):
+        nf, _, h, w = sample.shape
+        base = (sample.mean(1, keepdim=True) + 0.1 * controlnet_cond_latents.mean(1, keepdim=True)
+                + 0.01 * enc.mean((1, 2)).view(nf, 1, 1, 1)) * conditioning_scale * (1.0 + 1e-3 * float(t))
+        maps = [torch.nn.functional.avg_pool2d(base, ds).expand(nf, c, h // ds, w // ds).contiguous() * 0.05 if ds > 1
+                else base.expand(nf, c, h, w).contiguous() * 0.05 for c, ds in self.shapes]
+        return maps[:-1], maps[-1]
+
+
+def _loop_worker(rank, world, port, preset, out_path, cfg_split=False, with_controlnet=False):
     import torch.distributed as dist
     from musev_b200.pipeline import ParallelDenoiser
     from musev_b200.scheduler import SD15_DDIM_CONFIG, DDIMScheduler
@@ -108,9 +124,22 @@ def _loop_worker(rank, world, port, preset, out_path, cfg_split=False):
         return (o(sample, t, enc, **k),)
 
     den = ParallelDenoiser(unet, DDIMScheduler(**SD15_DDIM_CONFIG), device_ops=OracleOpsDouble)
+    cn_fn = None
+    if with_controlnet:
+        from musev_b200.pipeline import make_controlnet_fn
+        boc = m["block_out_channels"]
+        shapes, ds = [(boc[0], 1)], 1
+        for bi, ch in enumerate(boc):
+            shapes += [(ch, ds)] * 2
+            if bi != len(boc) - 1:
+                ds *= 2
+                shapes.append((ch, ds))
+        shapes.append((boc[-1], ds))
+        cn_lat = torch.randn(2, boc[0], 1 + m["T"], m["h"], m["w"], generator=gen)
+        cn_fn = make_controlnet_fn(_FakeControlNet(shapes), cn_lat, prompt, 1, controlnet_conditioning_scale=0.7)
     res = den(latents, cond, prompt, num_inference_steps=m["steps"], guidance_scale=m["guidance_scale"],
               context_frames=m["context_frames"], context_overlap=m["context_overlap"], motion_speed=8, unet_kwargs=kw,
-              cfg_split=cfg_split)
+              cfg_split=cfg_split, controlnet_fn=cn_fn)
     if rank == 0:
         torch.save({"latents": res.latents, "per_rank": res.windows_per_rank, "windows": res.windows}, out_path)
     if world > 1:
@@ -151,6 +180,13 @@ def test_parallel_denoise_two_ranks_gloo(tmp_path, preset):
     assert split["per_rank"] == [list(range(len(split["windows"])))]
     # a B-row forward and a 2B-row forward of the CPU oracle differ by fp32 blocking order (measured 2e-5)
     assert (split["latents"] - single["latents"]).abs().max().item() < 1e-4
+    # with a ControlNet callback: window slicing of the condition latents and, under CFG split, of the prompt / batch rows
+    p4, p5 = str(tmp_path / "w4.pt"), str(tmp_path / "w5.pt")
+    _loop_worker(0, 1, 0, preset, p4, False, True)
+    mp.spawn(_loop_worker, args=(2, _free_port(), preset, p5, True, True), nprocs=2, join=True)
+    cn1, cn2 = torch.load(p4), torch.load(p5)
+    assert (cn1["latents"] - single["latents"]).abs().max().item() > 1e-3      # the residuals matter
+    assert (cn2["latents"] - cn1["latents"]).abs().max().item() < 1e-4
 
 
 def test_closed_loop_window_with_repeated_frames_matches_reference_semantics():
