@@ -87,6 +87,12 @@ typedef struct mvb_attention_desc {
 } mvb_attention_desc;
 
 int mvb_op_attention(const mvb_attention_desc* desc, void* stream);
+/* Measurement aid (no reference equivalent): while `device_buffer` (>= 9*32*8 int64 on the device) is set, CTA (0,0,0) of every
+ * ping-pong attention launch (head dim <= 64) writes the SM clock at each phase of its first 32 key/value tiles:
+ * [role][tile][slot], role 4t+q = softmax warp of query tile t, lane quarter q (slots: 0 wait S, 1 S ready, 2 scores in registers, 3 row max,
+ * 4 exponentials done, 5 previous P.V complete, 6 P published), role 8 = the MMA-issuing warp (per query tile t, slots 4t..4t+3:
+ * S_t(j) freed, S_t(j+1) issued, P_t(j) ready, P_t(j)V(j) issued). NULL switches it off. tools/gpu_attention_trace.py. */
+int mvb_debug_attention_trace(long long* device_buffer);
 
 /* Temporal self-attention over the frame axis (musev/models/temporal_transformer.py:241-273 ->
  * musev/models/attention.py:293-365 -> AttnProcessor2_0). qkv: [B, T, HW, 3*heads*dp] (q | k | v). */

@@ -63,6 +63,8 @@ def _declare(l: C.CDLL) -> None:
     l.mvb_op_conv_gemm.restype = C.c_int
     l.mvb_op_attention.argtypes = [C.POINTER(AttentionDesc), C.c_void_p]
     l.mvb_op_attention.restype = C.c_int
+    l.mvb_debug_attention_trace.argtypes = [C.c_void_p]
+    l.mvb_debug_attention_trace.restype = C.c_int
     l.mvb_op_temporal_attention.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int,
                                             C.c_float, C.c_void_p, C.c_int, C.c_void_p]
     l.mvb_op_temporal_attention.restype = C.c_int

@@ -37,5 +37,7 @@ struct AttnArgs {
 };
 
 cudaError_t launch_attention(cudaStream_t stream, const AttnArgs& a, const char** err);
+// measurement aid: CTA (0,0,0) of the following ping-pong launches writes 10 x 32 x 8 clock64 stamps to device_buffer (null = off)
+void set_attention_trace(long long* device_buffer);
 
 }  // namespace mvb

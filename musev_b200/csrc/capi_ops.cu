@@ -73,6 +73,11 @@ int mvb_op_attention(const mvb_attention_desc* d, void* stream) {
   return MVB_OK;
 }
 
+int mvb_debug_attention_trace(long long* device_buffer) {
+  set_attention_trace(device_buffer);
+  return MVB_OK;
+}
+
 int mvb_op_temporal_attention(const void* qkv, int ld, int B, int T, int HW, int heads, int d, int dp, float scale,
                               void* out, int ldo, void* stream) {
   cudaError_t e = temporal_attention((cudaStream_t)stream, (const __half*)qkv, ld, B, T, HW, heads, d, dp, scale,

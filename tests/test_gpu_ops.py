@@ -146,11 +146,12 @@ def test_temporal_attention(ops, B, T, HW, d):
                                                     (4, 2, 256, 40, True, True), (4, 2, 256, 80, True, False),
                                                     (4, 2, 64, 160, True, False), (2, 1, 200, 40, False, True),
                                                     (2, 1, 16, 16, False, False), (6, 3, 1024, 40, True, True)])
-@pytest.mark.parametrize("variant", [0, 1, 2])
+@pytest.mark.parametrize("variant", [0, 1, 2, 4])
 def test_spatial_attention(ops, NF, T, Nq, d, viscond, ones, variant):
     """Reference-only self attention: K/V = own frame (+) first frame of the batch (attention_processor.py:431-493).
     variant 0 = default dispatch (ping-pong kernel with P in TMEM for padded head dims <= 64, the one-tile kernel above),
-    1 = the one-tile kernel everywhere, 2 = the split-KV kernel (padded head dims <= 64)."""
+    1 = the one-tile kernel everywhere, 2 = the split-KV kernel (padded head dims <= 64), 4 = the ping-pong kernel with two
+    threads per query row (padded head dims <= 64)."""
     torch.manual_seed(8)
     heads, dp, M = 8, (d + 15) // 16 * 16, NF * Nq
     q, k, v = (torch.randn(M, heads * d, device=dev).half() for _ in range(3))
