@@ -1421,17 +1421,19 @@ cudaError_t launch_attention(cudaStream_t stream, const AttnArgs& a, const char*
   // ping-pong kernel (two query tiles per CTA, P in TMEM) for one-atom head dims; variant 1 / MVB_ATTN=1 forces the
   // previous kernel for A/B runs
   if (a.dp <= 64 && a.variant != 1 && attn_env != 1) {
-    static const KernelFn pp_kernels[2][4] = {
-        {attention_pp_kernel<false, 0, false>, attention_pp_kernel<false, 2, false>, attention_pp_kernel<false, 3, false>, attention_pp_kernel<false, 4, false>},
-        {attention_pp_kernel<true, 0, false>, attention_pp_kernel<true, 2, false>, attention_pp_kernel<true, 3, false>, attention_pp_kernel<true, 4, false>}};
+    static const KernelFn pp_kernels[2][5] = {
+        {attention_pp_kernel<false, 0, false>, attention_pp_kernel<false, 1, false>, attention_pp_kernel<false, 2, false>,
+         attention_pp_kernel<false, 3, false>, attention_pp_kernel<false, 4, false>},
+        {attention_pp_kernel<true, 0, false>, attention_pp_kernel<true, 1, false>, attention_pp_kernel<true, 2, false>,
+         attention_pp_kernel<true, 3, false>, attention_pp_kernel<true, 4, false>}};
     static const int pp_poly_env = getenv("MVB_POLY") ? atoi(getenv("MVB_POLY")) : 2;
-    const int pp_idx = pp_poly_env <= 0 ? 0 : pp_poly_env == 2 ? 1 : pp_poly_env >= 4 ? 3 : 2;
+    const int pp_idx = pp_poly_env <= 0 ? 0 : pp_poly_env >= 4 ? 4 : pp_poly_env;   // FMA-pipe share of the exponentials, n/8
     const int smem_pp = (2 + 2 * kPpStages) * kAtomBytes + 1024 + 512;
     static bool pp_set_dev[64] = {};
     if (!pp_set_dev[cur_dev & 63]) {
       cudaError_t e = cudaSuccess;
       for (int x = 0; x < 2 && e == cudaSuccess; ++x)
-        for (int y = 0; y < 4 && e == cudaSuccess; ++y)
+        for (int y = 0; y < 5 && e == cudaSuccess; ++y)
           e = cudaFuncSetAttribute(reinterpret_cast<const void*>(pp_kernels[x][y]), cudaFuncAttributeMaxDynamicSharedMemorySize, smem_pp);
       if (e != cudaSuccess) { *err = "cudaFuncSetAttribute(attention_pp_kernel)"; return e; }
       pp_set_dev[cur_dev & 63] = true;
@@ -1458,12 +1460,13 @@ cudaError_t launch_attention(cudaStream_t stream, const AttnArgs& a, const char*
         if (e != cudaSuccess) { *err = "cudaFuncSetAttribute(attention_pp2_kernel)"; return e; }
         pp2_set_dev[cur_dev & 63] = true;
       }
-      pp2_kernels[p.sum_in_v ? 1 : 0][pp_idx]<<<grid_pp, 576, smem_pp2, stream>>>(tq, tk0, tv0, tk1, tv1, p);
+      const int pp2_idx = pp_idx == 0 ? 0 : pp_idx <= 2 ? 1 : pp_idx == 3 ? 2 : 3;
+      pp2_kernels[p.sum_in_v ? 1 : 0][pp2_idx]<<<grid_pp, 576, smem_pp2, stream>>>(tq, tk0, tv0, tk1, tv1, p);
       cudaError_t e = cudaGetLastError();
       if (e != cudaSuccess) *err = "attention_pp2_kernel launch";
       return e;
     }
-    if (p.trace != nullptr && p.sum_in_v && pp_idx == 1) {   // traced build of the default instantiation (mvb_debug_attention_trace)
+    if (p.trace != nullptr && p.sum_in_v && pp_idx == 2) {   // traced build of the default instantiation (mvb_debug_attention_trace)
       const KernelFn traced = attention_pp_kernel<true, 2, true>;
       cudaError_t e = cudaFuncSetAttribute(reinterpret_cast<const void*>(traced), cudaFuncAttributeMaxDynamicSharedMemorySize, smem_pp);
       if (e != cudaSuccess) { *err = "cudaFuncSetAttribute(attention_pp_kernel, traced)"; return e; }

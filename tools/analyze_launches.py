@@ -21,7 +21,7 @@ agg = {}
 bycat = collections.defaultdict(float)
 for kn, t in rows:
     key = kn
-    if kn.startswith("conv_gemm") or kn.startswith("attention_kernel"):
+    if kn.startswith("conv_gemm") or kn.startswith("attention_"):
         want = "gemm" if kn.startswith("conv_gemm") else "attn"
         while ti < len(trace) and not trace[ti].startswith(want):
             ti += 1
