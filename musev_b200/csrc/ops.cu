@@ -186,6 +186,40 @@ __global__ void gn_finalize_kernel(const float* __restrict__ part, int chunks, i
   gn_finalize_unit(part, chunks, fps, G, HW, cpg, eps, stats, blockIdx.x, blockIdx.y, threadIdx.x);
 }
 
+// 5-D statistics (fps = T frames per group of statistics) have fps x chunks partials per channel group -- 578 at level 0, which
+// one warp walks in 18.6 us (ncu, profiles/r02_ncu_kernels_full_summary.txt), and 104 of the 166 GroupNorms of a forward are
+// of this kind. Same reduction on kGnFinalizeWarps warps: every thread merges its strided share, a fixed butterfly per warp,
+// then warp 0 merges the warp results in index order -- deterministic.
+static constexpr int kGnFinalizeWarps = 8;
+__global__ void __launch_bounds__(kGnFinalizeWarps * 32)
+gn_finalize_wide_kernel(const float* __restrict__ part, int chunks, int fps, int G, int HW, int cpg, float eps,
+                        float* __restrict__ stats) {
+  __shared__ float sred[kGnFinalizeWarps][3];
+  const int sg = blockIdx.x, g = blockIdx.y, warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  float n = 0.f, mean = 0.f, m2 = 0.f;
+  for (int i = threadIdx.x; i < fps * chunks; i += kGnFinalizeWarps * 32) {
+    const int chunk = i % chunks;
+    const int pix = (int)(((long long)HW * (chunk + 1)) / chunks) - (int)(((long long)HW * chunk) / chunks);
+    const float2 pp = *reinterpret_cast<const float2*>(part + ((size_t)sg * fps * chunks + i) * 2 * G + 2 * g);
+    chan_merge(n, mean, m2, (float)pix * (float)cpg, pp.x, pp.y);
+  }
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) {
+    const float nb = __shfl_xor_sync(0xffffffffu, n, o);
+    const float mb = __shfl_xor_sync(0xffffffffu, mean, o);
+    const float qb = __shfl_xor_sync(0xffffffffu, m2, o);
+    chan_merge(n, mean, m2, nb, mb, qb);
+  }
+  if (lane == 0) { sred[warp][0] = n; sred[warp][1] = mean; sred[warp][2] = m2; }
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    for (int w = 1; w < kGnFinalizeWarps; ++w) chan_merge(n, mean, m2, sred[w][0], sred[w][1], sred[w][2]);
+    const float var = n > 0.f ? fmaxf(m2 / n, 0.f) : 0.f;
+    stats[((size_t)sg * G + g) * 2] = mean;
+    stats[((size_t)sg * G + g) * 2 + 1] = rsqrtf(var + eps);
+  }
+}
+
 // grid (pixel blocks, NF); block 256; each block streams ~64 KB.
 __device__ __forceinline__ void gn_apply_unit(const __half* __restrict__ x0, int C0, const __half* __restrict__ x1, int C1, int HW,
                                               int G, const float* __restrict__ stats, int fps, const float* __restrict__ gamma,
@@ -284,7 +318,7 @@ gn_apply_kernel(const __half* __restrict__ x0, int C0, const __half* __restrict_
 // All blocks are co-resident (grid = occupancy x SMs), so a software barrier on a global counter is safe. The apply phase
 // walks the frames in the opposite order of the statistics phase, i.e. it starts with the frames the statistics phase read
 // last, which are still in L2 (126 MB): up to ~2/3 of the second read of a level-0 tensor (89 MB) no longer goes to HBM, and
-// two launches per GroupNorm (332 per forward) disappear. Bit-identical to the three-kernel path (same partial layout, same
+// two launches per GroupNorm (332 per forward) disappear. Bit-identical to the three-kernel path for 4-D statistics (same partial layout, same
 // fixed-order reductions).
 __device__ __forceinline__ void gn_grid_barrier(unsigned int* counter, unsigned int target) {
   __syncthreads();
@@ -342,7 +376,8 @@ cudaError_t gn_apply(cudaStream_t s, const __half* x0, int C0, const __half* x1,
   if (fps < 1 || (NF % fps) || G > 64) return cudaErrorInvalidValue;
   // mean / rstd live right behind the partial sums in the caller's scratch: NF*(kGnMaxChunks+1)*G*2 floats in total
   float* stats = const_cast<float*>(part) + (size_t)NF * kGnMaxChunks * G * 2;
-  gn_finalize_kernel<<<dim3(NF / fps, G), 32, 0, s>>>(part, chunks, fps, G, HW, C / G, eps, stats);
+  if (fps * chunks > 64) gn_finalize_wide_kernel<<<dim3(NF / fps, G), kGnFinalizeWarps * 32, 0, s>>>(part, chunks, fps, G, HW, C / G, eps, stats);
+  else gn_finalize_kernel<<<dim3(NF / fps, G), 32, 0, s>>>(part, chunks, fps, G, HW, C / G, eps, stats);
   // ~64 KB of fp16 per block, block size a multiple of the number of channel vectors when possible
   const int vecs = C / 8;
   int threads = 256;

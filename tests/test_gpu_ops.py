@@ -111,8 +111,13 @@ def test_groupnorm(ops, NF, HW, C0, C1, fps, silu, fused):
     C = C0 + C1
     g, b = torch.randn(C, device=dev), torch.randn(C, device=dev)
     y = ops.groupnorm(x0, g, b, 32, fps, 1e-5, silu, x1, fused=fused)
-    if fused:      # one launch vs three launches: same partial layout and reduction order -> bit-identical
-        assert torch.equal(y, ops.groupnorm(x0, g, b, 32, fps, 1e-5, silu, x1)) and torch.equal(y, ops.groupnorm(x0, g, b, 32, fps, 1e-5, silu, x1, fused=True))
+    if fused:      # one launch vs three launches: same partial layout; deterministic
+        assert torch.equal(y, ops.groupnorm(x0, g, b, 32, fps, 1e-5, silu, x1, fused=True))
+        y3 = ops.groupnorm(x0, g, b, 32, fps, 1e-5, silu, x1)
+        if fps == 1:   # same reduction order -> bit-identical (the three-launch path merges 5-D statistics on 8 warps instead of 1)
+            assert torch.equal(y, y3)
+        else:
+            assert (y.float() - y3.float()).abs().max().item() <= 4e-3
     x = x0 if x1 is None else torch.cat([x0, x1], 2)
     ref = F.group_norm(x.float().view(NF // fps, fps * HW, C).permute(0, 2, 1), 32, g, b, 1e-5)
     if silu:

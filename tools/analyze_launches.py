@@ -14,7 +14,7 @@ for row in csv.DictReader(io.StringIO("".join(lines))):
     v = float(row["Metric Value"].replace(",", ""))
     u = row["Metric Unit"]
     v = v / 1e6 if u == "ns" else v / 1e3 if u == "us" else v
-    rows.append((row["Kernel Name"].split("(")[0].replace("void ", ""), v))
+    rows.append((row["Kernel Name"].split("(")[0].replace("void ", "").replace("mvb::", ""), v))
 trace = [l.strip().replace("MVB_TRACE ", "") for l in open(log_path) if l.startswith("MVB_TRACE")]
 ti = 0
 agg = {}
