@@ -1,20 +1,23 @@
-// tcgen05 flash attention (see attention.cuh). One CTA = 320 threads = 128 queries of one (frame, head).
+// tcgen05 flash attention (see attention.cuh). Four kernels, selected in launch_attention():
 //
-//   warp 0      : TMA producer (Q once; K ring one tile ahead; V ring) -- boxes of 128 rows x 64 fp16, 128-byte swizzle;
-//                 warp-uniform loop, elect.sync picks the issuing lane
-//   warp 1      : TMEM allocator + MMA issuer (warp-uniform loop, one elected lane issues)
-//                   S = Q K^T   (M=128 queries, N=128 keys, K=dp)      -> TMEM columns [0,128); S_{j+1} is issued as
-//                               soon as the softmax warps hold S_j in registers, i.e. it runs under softmax j
-//                   O += P V    (M=128, N=dp, K=128 keys; V consumed MN-major straight from its row-major tile)
-//   warps 2..9  : softmax, two threads per query row (64 key columns each): tcgen05.ld S into registers, online max
-//                 (the two halves of a row pair exchange it through smem behind a 64-thread named barrier) with lazy
-//                 rescaling of the TMEM accumulator (only when the running max grows by > 2^8), exp2 on packed f32x2
-//                 arguments with a fixed share on the FMA pipe (degree-3 polynomial) and the rest on the SFU,
-//                 P -> fp16 -> swizzled smem as MMA A operand; row sums come from the MMA (ones column in V)
-// Two CTAs are resident per SM when the head dimension allows (dp <= 64). At d = 40 the kernel is bound by the
-// dependent-issue latency of the softmax (4 softmax warps per scheduler at 96 registers), not by a pipe: DESIGN.md 4.2.
-// A split-KV variant (two independent 4-warp softmax groups on alternating 64-key tiles) follows the main kernel; it is
-// correct but slower and only runs on request (AttnArgs.variant = 2).
+//   attention_pp_kernel   head dims that fit one 64-column atom (dp <= 64: level 0 of the UNet, 75 % of the attention time).
+//                         One CTA per SM = 256 queries = two 128-query tiles ping-ponged on one MMA-issuing warp, one thread per
+//                         query row, P kept in TMEM (TS-form P.V). Description, measurements and the phase trace: the comment
+//                         above the kernel and DESIGN.md 4.2. attention_pp2_kernel (variant 4) = the same with two threads per row.
+//   attention_kernel      head dims 80 / 160 (and variant 1 for A/B runs). One CTA = 320 threads = 128 queries of one (frame, head):
+//     warp 0      : TMA producer (Q once; K ring one tile ahead; V ring) -- boxes of 128 rows x 64 fp16, 128-byte swizzle;
+//                   warp-uniform loop, elect.sync picks the issuing lane
+//     warp 1      : TMEM allocator + MMA issuer (warp-uniform loop, one elected lane issues)
+//                     S = Q K^T   (M=128 queries, N=128 keys, K=dp)      -> TMEM columns [0,128); S_{j+1} is issued as
+//                                 soon as the softmax warps hold S_j in registers, i.e. it runs under softmax j
+//                     O += P V    (M=128, N=dp, K=128 keys; V consumed MN-major straight from its row-major tile)
+//     warps 2..9  : softmax, two threads per query row (64 key columns each): tcgen05.ld S into registers, online max
+//                   (the two halves of a row pair exchange it through smem behind a 64-thread named barrier) with lazy
+//                   rescaling of the TMEM accumulator (only when the running max grows by > 2^8), exp2 on packed f32x2
+//                   arguments with a fixed share on the FMA pipe (degree-3 polynomial) and the rest on the SFU,
+//                   P -> fp16 -> swizzled smem as MMA A operand; row sums come from the MMA (ones column in V)
+//   attention_split_kernel  split-KV variant of attention_kernel (two independent 4-warp softmax groups on alternating 64-key
+//                         tiles); correct but slower, only on request (AttnArgs.variant = 2).
 #include "attention.cuh"
 
 #include <cuda.h>

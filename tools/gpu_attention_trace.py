@@ -57,7 +57,7 @@ def main():
             e["period"] = round(float((r[lo + 1:hi + 1, 1] - r[lo:hi, 1]).mean()))
             e["busy"] = round(float((r[lo:hi, 6] - r[lo:hi, 1]).mean()))
             res[f"softmax_t{t}_q{q}"] = e
-    two = bool((rel[9] != 0).any())                   # one MMA warp per query tile (default) / one for both (MVB_PP_MMA_WARPS=1)
+    two = bool((rel[9] != 0).any())                   # stamps of a second MMA-issuing warp (an experiment of round 2; the shipped kernel has one)
     for t in range(2):
         m = rel[8 + t].double() if two else rel[8].double()
         b = 0 if two else 4 * t
