@@ -93,6 +93,11 @@ int mvb_op_attention(const mvb_attention_desc* desc, void* stream);
  * 4 exponentials done, 5 previous P.V complete, 6 P published), role 8 = the MMA-issuing warp (per query tile t, slots 4t..4t+3:
  * S_t(j) freed, S_t(j+1) issued, P_t(j) ready, P_t(j)V(j) issued). NULL switches it off. tools/gpu_attention_trace.py. */
 int mvb_debug_attention_trace(long long* device_buffer);
+/* Encoded TMA descriptors (cuTensorMapEncodeTiled: 2-6 per GEMM / convolution, 5 per attention call) are memoized process-wide by
+ * (address, extents, strides, box, swizzle); the engine's workspace arena reproduces its addresses on every forward of the same
+ * shapes, so from the second window-step on they are hash lookups. Hits / misses since the library was loaded (no reference
+ * equivalent; MVB_TMAP_CACHE=0 disables the cache). */
+int mvb_tensor_map_cache_stats(unsigned long long* hits, unsigned long long* misses);
 
 /* Temporal self-attention over the frame axis (musev/models/temporal_transformer.py:241-273 ->
  * musev/models/attention.py:293-365 -> AttnProcessor2_0). qkv: [B, T, HW, 3*heads*dp] (q | k | v). */

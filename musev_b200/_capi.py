@@ -65,6 +65,8 @@ def _declare(l: C.CDLL) -> None:
     l.mvb_op_attention.restype = C.c_int
     l.mvb_debug_attention_trace.argtypes = [C.c_void_p]
     l.mvb_debug_attention_trace.restype = C.c_int
+    l.mvb_tensor_map_cache_stats.argtypes = [C.POINTER(C.c_ulonglong), C.POINTER(C.c_ulonglong)]
+    l.mvb_tensor_map_cache_stats.restype = C.c_int
     l.mvb_op_temporal_attention.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int,
                                             C.c_float, C.c_void_p, C.c_int, C.c_void_p]
     l.mvb_op_temporal_attention.restype = C.c_int
@@ -111,6 +113,13 @@ def launch_count(category: int = -1) -> int:
 
 def profile_enable(on: bool) -> None:
     lib().mvb_profile_enable(int(on))
+
+
+def tensor_map_cache_stats():
+    """(hits, misses) of the process-wide memo of encoded TMA descriptors."""
+    h, m = C.c_ulonglong(0), C.c_ulonglong(0)
+    check(lib().mvb_tensor_map_cache_stats(C.byref(h), C.byref(m)))
+    return int(h.value), int(m.value)
 
 
 def profile_collect():

@@ -73,6 +73,12 @@ int mvb_op_attention(const mvb_attention_desc* d, void* stream) {
   return MVB_OK;
 }
 
+int mvb_tensor_map_cache_stats(unsigned long long* hits, unsigned long long* misses) {
+  if (!hits || !misses) return fail("mvb_tensor_map_cache_stats: null pointer", cudaSuccess);
+  tensor_map_cache_stats(hits, misses);
+  return MVB_OK;
+}
+
 int mvb_debug_attention_trace(long long* device_buffer) {
   set_attention_trace(device_buffer);
   return MVB_OK;

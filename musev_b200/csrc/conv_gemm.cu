@@ -16,6 +16,9 @@
 #include <dlfcn.h>
 #include <stdio.h>
 #include <stdlib.h>
+#include <string.h>
+
+#include <mutex>
 
 #include "ptx.cuh"
 #include "stats.cuh"
@@ -518,19 +521,107 @@ EncodeTiledFn get_encode_fn() {
   return fn;
 }
 
-// rank-4 fp16 map, inner box 64 elements, 128-byte swizzle, zero fill out of bounds
-bool encode_map_4d_sw(CUtensorMap* m, const void* ptr, const uint64_t dims[4], const uint64_t strides_elems[3],
-                      const uint32_t box[4], CUtensorMapSwizzle swz) {
+// ---- encoded tensor maps are memoized. A CUtensorMap is a pure function of (address, extents, strides, box, swizzle); the engine's
+// bump arena hands out the same addresses for the same shapes on every forward, so after the first window-step every one of the
+// ~2 500 cuTensorMapEncodeTiled calls of a forward (2-6 per GEMM, 5 per attention; VERDICT r01 "host encodes tensor maps per launch")
+// becomes a hash lookup. Open addressing on 2^14 slots, cleared wholesale when 3/4 full (callers that stream fresh torch
+// buffers through the op-level ABI only ever cost themselves re-encodes). MVB_TMAP_CACHE=0 switches it off (A/B runs).
+namespace {
+struct MapKey {
+  uint64_t ptr, d[4], s[3];
+  uint32_t box[4], rank, swz;
+  bool operator==(const MapKey& o) const { return memcmp(this, &o, sizeof(MapKey)) == 0; }
+};
+struct MapSlot {
+  MapKey key;
+  CUtensorMap map;
+  bool used;
+};
+static_assert(sizeof(MapKey) == 88, "MapKey is compared and hashed bytewise: no padding allowed");
+static_assert(sizeof(MapSlot) % 64 == 0, "slots keep the 64-byte alignment of CUtensorMap");
+constexpr uint32_t kMapSlots = 1u << 14;
+std::mutex g_map_mutex;
+MapSlot* g_map_slots = nullptr;
+uint32_t g_map_count = 0;
+unsigned long long g_map_hits = 0, g_map_misses = 0;
+
+uint64_t hash_key(const MapKey& k) {
+  const uint64_t* w = reinterpret_cast<const uint64_t*>(&k);
+  uint64_t h = 0x9e3779b97f4a7c15ull;
+  for (size_t i = 0; i < sizeof(MapKey) / 8; ++i) {
+    h ^= w[i] + 0x9e3779b97f4a7c15ull + (h << 6) + (h >> 2);
+    h *= 0xff51afd7ed558ccdull;
+    h ^= h >> 33;
+  }
+  return h;
+}
+bool cache_enabled() {
+  static const bool on = !(getenv("MVB_TMAP_CACHE") && atoi(getenv("MVB_TMAP_CACHE")) == 0);
+  return on;
+}
+
+bool encode_raw(CUtensorMap* m, const MapKey& k) {
   EncodeTiledFn fn = get_encode_fn();
   if (!fn) return false;
-  cuuint64_t gd[4] = {dims[0], dims[1], dims[2], dims[3]};
-  cuuint64_t gs[3] = {strides_elems[0] * 2, strides_elems[1] * 2, strides_elems[2] * 2};
-  cuuint32_t bx[4] = {box[0], box[1], box[2], box[3]};
+  cuuint64_t gd[4] = {k.d[0], k.d[1], k.d[2], k.d[3]};
+  cuuint64_t gs[3] = {k.s[0] * 2, k.s[1] * 2, k.s[2] * 2};
+  cuuint32_t bx[4] = {k.box[0], k.box[1], k.box[2], k.box[3]};
   cuuint32_t es[4] = {1, 1, 1, 1};
-  CUresult r = fn(m, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 4, const_cast<void*>(ptr), gd, gs, bx, es,
-                  CU_TENSOR_MAP_INTERLEAVE_NONE, swz, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+  CUresult r = fn(m, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, k.rank, reinterpret_cast<void*>(k.ptr), gd, gs, bx, es,
+                  CU_TENSOR_MAP_INTERLEAVE_NONE, (CUtensorMapSwizzle)k.swz, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
                   CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
   return r == CUDA_SUCCESS;
+}
+
+bool encode_cached(CUtensorMap* m, const MapKey& k) {
+  if (!cache_enabled()) return encode_raw(m, k);
+  std::lock_guard<std::mutex> lock(g_map_mutex);
+  if (!g_map_slots) {                                // CUtensorMap is alignas(64): aligned_alloc, not calloc
+    g_map_slots = static_cast<MapSlot*>(aligned_alloc(64, sizeof(MapSlot) * kMapSlots));
+    if (g_map_slots) memset(g_map_slots, 0, sizeof(MapSlot) * kMapSlots);
+  }
+  if (!g_map_slots) return encode_raw(m, k);
+  uint32_t i = (uint32_t)hash_key(k) & (kMapSlots - 1);
+  while (g_map_slots[i].used) {
+    if (g_map_slots[i].key == k) {
+      *m = g_map_slots[i].map;
+      ++g_map_hits;
+      return true;
+    }
+    i = (i + 1) & (kMapSlots - 1);
+  }
+  if (!encode_raw(m, k)) return false;
+  ++g_map_misses;
+  if (g_map_count >= kMapSlots / 4 * 3) {            // full: start over (the live working set re-enters within one forward)
+    memset(g_map_slots, 0, sizeof(MapSlot) * kMapSlots);
+    g_map_count = 0;
+    i = (uint32_t)hash_key(k) & (kMapSlots - 1);
+  }
+  g_map_slots[i].key = k;
+  g_map_slots[i].map = *m;
+  g_map_slots[i].used = true;
+  ++g_map_count;
+  return true;
+}
+}  // namespace
+
+void tensor_map_cache_stats(unsigned long long* hits, unsigned long long* misses) {
+  std::lock_guard<std::mutex> lock(g_map_mutex);
+  *hits = g_map_hits;
+  *misses = g_map_misses;
+}
+
+// rank-4 fp16 map, inner box 64 elements, swizzle as given, zero fill out of bounds
+bool encode_map_4d_sw(CUtensorMap* m, const void* ptr, const uint64_t dims[4], const uint64_t strides_elems[3],
+                      const uint32_t box[4], CUtensorMapSwizzle swz) {
+  MapKey k;
+  memset(&k, 0, sizeof(k));                          // the key is compared bytewise: no uninitialised padding
+  k.ptr = reinterpret_cast<uint64_t>(ptr);
+  for (int i = 0; i < 4; ++i) { k.d[i] = dims[i]; k.box[i] = box[i]; }
+  for (int i = 0; i < 3; ++i) k.s[i] = strides_elems[i];
+  k.rank = 4;
+  k.swz = (uint32_t)swz;
+  return encode_cached(m, k);
 }
 bool encode_map_4d(CUtensorMap* m, const void* ptr, const uint64_t dims[4], const uint64_t strides_elems[3],
                    const uint32_t box[4]) {
@@ -539,16 +630,15 @@ bool encode_map_4d(CUtensorMap* m, const void* ptr, const uint64_t dims[4], cons
 
 bool encode_map_2d(CUtensorMap* m, const void* ptr, uint64_t d0, uint64_t d1, uint64_t stride1_elems, uint32_t b0,
                    uint32_t b1) {
-  EncodeTiledFn fn = get_encode_fn();
-  if (!fn) return false;
-  cuuint64_t gd[2] = {d0, d1};
-  cuuint64_t gs[1] = {stride1_elems * 2};
-  cuuint32_t bx[2] = {b0, b1};
-  cuuint32_t es[2] = {1, 1};
-  CUresult r = fn(m, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 2, const_cast<void*>(ptr), gd, gs, bx, es,
-                  CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
-                  CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
-  return r == CUDA_SUCCESS;
+  MapKey k;
+  memset(&k, 0, sizeof(k));
+  k.ptr = reinterpret_cast<uint64_t>(ptr);
+  k.d[0] = d0; k.d[1] = d1;
+  k.s[0] = stride1_elems;
+  k.box[0] = b0; k.box[1] = b1;
+  k.rank = 2;
+  k.swz = (uint32_t)CU_TENSOR_MAP_SWIZZLE_128B;
+  return encode_cached(m, k);
 }
 
 static int ceil_div(int a, int b) { return (a + b - 1) / b; }

@@ -76,4 +76,7 @@ cudaError_t launch_conv_gemm(cudaStream_t stream, const ASource& a0, const ASour
 cudaError_t launch_conv_s2(cudaStream_t stream, const __half* x, int C, int W, int H, int NF, const __half* wt, int N,
                            const Epilogue& ep, int num_sms, const char** err);
 
+// Encoded tensor maps are memoized process-wide (conv_gemm.cu): hits / misses since the library was loaded.
+void tensor_map_cache_stats(unsigned long long* hits, unsigned long long* misses);
+
 }  // namespace mvb

@@ -303,3 +303,27 @@ def test_full_width_other_window_shapes_vs_fp32_oracle(built_lib, preset, frames
     # the max over 10^6..10^7 outputs sits higher than in the small-shape test (measured 1.3e-2 for musev_referencenet at
     # 64x64); what matters is that the engine is no further from fp32 than the reference's own fp16 arithmetic
     assert torch.isfinite(out).all() and err < 2.5e-2 and rms < 1.2 * rms16 and err < 1.5 * err16, (err, err16, rms, rms16)
+
+
+def test_tensor_map_cache_hits_on_repeated_forward(built_lib):
+    """Encoded TMA descriptors are memoized: the second forward of the same shapes through the same workspace re-uses them
+    (hits, a handful of misses for freshly allocated torch outputs at most) and reproduces the first bit for bit."""
+    import os
+    from musev_b200 import _capi
+    from musev_b200.unet import UNet3DConditionModel
+    if os.environ.get("MVB_TMAP_CACHE") == "0":
+        pytest.skip("cache disabled by MVB_TMAP_CACHE=0")
+    cfg = preset_config("musev", block_out_channels=(64, 128, 128, 128))
+    model = UNet3DConditionModel(cfg, device=dev, dtype=torch.float16)
+    model.load_state_dict(make_state_dict(cfg, seed=0, dtype=torch.float16))
+    inp = make_inputs(cfg, batch=2, frames=8, h=16, w=16, n_vis_cond=1, seed=3)
+    kw = _call_kwargs(inp, 8, 1.0)
+    x, enc = inp["sample"].to(dev).half(), inp["encoder_hidden_states"].to(dev).half()
+    kw = {k: _to(v, dev, torch.float16) for k, v in kw.items()}
+    a = model(x, 301, enc, **kw).sample.clone()
+    h0, m0 = _capi.tensor_map_cache_stats()
+    b = model(x, 301, enc, **kw).sample.clone()
+    h1, m1 = _capi.tensor_map_cache_stats()
+    torch.cuda.synchronize()
+    assert torch.equal(a, b)
+    assert h1 - h0 > 500 and (m1 - m0) * 20 < (h1 - h0), (h0, m0, h1, m1)

@@ -43,11 +43,21 @@ def main():
     e1.record()
     torch.cuda.synchronize()
     ms = e0.elapsed_time(e1) / a.iters
+    import time
+    host = []
+    for _ in range(3):                       # host time to enqueue ONE forward into an empty stream
+        torch.cuda.synchronize()
+        t0 = time.perf_counter()
+        m(x, 601, enc, **kw)
+        host.append((time.perf_counter() - t0) * 1e3)
+    torch.cuda.synchronize()
+    hits, misses = _capi.tensor_map_cache_stats()
     _capi.profile_enable(True)
     m(x, 601, enc, **kw)
     prof = _capi.profile_collect()
     _capi.profile_enable(False)
-    print("FWD_TIME " + json.dumps({"tag": a.tag, "preset": a.preset, "ms": ms,
+    print("FWD_TIME " + json.dumps({"tag": a.tag, "preset": a.preset, "ms": ms, "host_enqueue_ms": round(min(host), 2),
+                                    "tensor_map_cache": {"hits": hits, "misses": misses},
                                     "split_ms": {k: round(v["ms"], 2) for k, v in prof.items()},
                                     "launches": {k: v["launches"] for k, v in prof.items()}}), flush=True)
 
