@@ -30,8 +30,6 @@ static constexpr int kBlockM = 128;
 static constexpr int kBlockK = 64;
 static constexpr int kMaxBlockN = 256;
 static constexpr int kABytes = kBlockM * kBlockK * 2;        // 16 KB
-static constexpr int kBBytes = kMaxBlockN * kBlockK * 2;     // 32 KB
-static constexpr int kStageBytes = kABytes + kBBytes;
 static constexpr int kStagingBufBytes = 128 * 64;               // 128 rows x 32 fp16 output columns
 static constexpr int kStagingDepth = 4;                         // staging buffers per column half (3 TMA stores in flight)
 static constexpr int kStagingBytes = 2 * kStagingDepth * kStagingBufBytes;
@@ -325,7 +323,6 @@ conv_gemm_kernel(const __grid_constant__ AMaps tmA, const __grid_constant__ CUte
               if constexpr (kEpi == kEpiGeglu) {
                 // output columns 8g..8g+7 of this chunk: accumulator block g/2 (va | vb), value j, gate 16 + j
                 const uint32_t* vv = (g < 2) ? v : vg;
-                const int nb = nbase + (g >> 1) * 32;
                 const int j0 = (g & 1) * 8;
 #pragma unroll
                 for (int e = 0; e < 4; ++e) {
