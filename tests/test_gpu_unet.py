@@ -321,9 +321,14 @@ def test_tensor_map_cache_hits_on_repeated_forward(built_lib):
     x, enc = inp["sample"].to(dev).half(), inp["encoder_hidden_states"].to(dev).half()
     kw = {k: _to(v, dev, torch.float16) for k, v in kw.items()}
     a = model(x, 301, enc, **kw).sample.clone()
-    h0, m0 = _capi.tensor_map_cache_stats()
-    b = model(x, 301, enc, **kw).sample.clone()
-    h1, m1 = _capi.tensor_map_cache_stats()
-    torch.cuda.synchronize()
-    assert torch.equal(a, b)
-    assert h1 - h0 > 500 and (m1 - m0) * 20 < (h1 - h0), (h0, m0, h1, m1)
+    ok = False
+    for _ in range(3):      # the process-wide table is cleared wholesale when it fills up: that may fall into one attempt
+        h0, m0 = _capi.tensor_map_cache_stats()
+        b = model(x, 301, enc, **kw).sample.clone()
+        h1, m1 = _capi.tensor_map_cache_stats()
+        torch.cuda.synchronize()
+        assert torch.equal(a, b)
+        if h1 - h0 > 500 and (m1 - m0) * 20 < (h1 - h0):
+            ok = True
+            break
+    assert ok, (h0, m0, h1, m1)
