@@ -44,3 +44,32 @@ def test_product_does_not_import_oracle():
             if f.endswith((".py", ".cu", ".cuh", ".h")):
                 txt = open(os.path.join(dirpath, f)).read()
                 assert "from oracle" not in txt and "import oracle" not in txt, f
+
+
+def test_struct_layouts_match_ctypes_mirrors(tmp_path):
+    """Every struct of include/musev_b200.h against its ctypes mirror: size and the offset of every field, as a C compiler sees
+    them (gcc on the header alone -- the boundary is plain C). Guards the Python binding against silent ABI drift."""
+    from musev_b200 import _capi, controlnet, unet, vae
+    mirrors = {"mvb_conv_gemm_desc": _capi.ConvGemmDesc, "mvb_attention_desc": _capi.AttentionDesc, "mvb_config": unet.MvbConfig,
+               "mvb_unet_args": unet.MvbUnetArgs, "mvb_named_tensor": unet.MvbNamedTensor,
+               "mvb_controlnet_args": controlnet.MvbControlnetArgs, "mvb_vae_decode_args": vae.MvbVaeDecodeArgs}
+    header = open(os.path.join(ROOT, "include", "musev_b200.h")).read()
+    declared = set(re.findall(r"^\}\s*(mvb_[a-z_]+);", header, flags=re.M))
+    assert declared == set(mirrors), declared ^ set(mirrors)
+    lines = ['#include <stdio.h>', '#include <stddef.h>', '#include "musev_b200.h"', "int main(void) {"]
+    for cname, cls in mirrors.items():
+        lines.append(f'  printf("{cname} . %zu\\n", sizeof({cname}));')
+        for fname, *_ in cls._fields_:
+            lines.append(f'  printf("{cname} {fname} %zu\\n", offsetof({cname}, {fname}));')
+    lines += ["  return 0;", "}"]
+    src = tmp_path / "layout.c"
+    src.write_text("\n".join(lines))
+    exe = tmp_path / "layout"
+    r = subprocess.run(["gcc", "-std=c11", "-I", os.path.join(ROOT, "include"), str(src), "-o", str(exe)], capture_output=True, text=True)
+    assert r.returncode == 0, r.stderr
+    out = subprocess.run([str(exe)], capture_output=True, text=True, check=True).stdout
+    for line in out.strip().splitlines():
+        cname, fname, value = line.split()
+        cls = mirrors[cname]
+        expect = ctypes.sizeof(cls) if fname == "." else getattr(cls, fname).offset
+        assert int(value) == expect, (cname, fname, int(value), expect)
