@@ -73,3 +73,31 @@ def test_struct_layouts_match_ctypes_mirrors(tmp_path):
         cls = mirrors[cname]
         expect = ctypes.sizeof(cls) if fname == "." else getattr(cls, fname).offset
         assert int(value) == expect, (cname, fname, int(value), expect)
+
+
+def _prototypes():
+    """name -> number of parameters, parsed from the header (comments stripped; `void` = 0)."""
+    src = open(os.path.join(ROOT, "include", "musev_b200.h")).read()
+    src = re.sub(r"/\*.*?\*/", "", src, flags=re.S)
+    protos = {}
+    for m in re.finditer(r"\b(mvb_[a-z0-9_]+)\s*\(([^()]*)\)\s*;", src):
+        args = m.group(2).strip()
+        protos[m.group(1)] = 0 if args in ("", "void") else args.count(",") + 1
+    return protos
+
+
+def test_ctypes_argtypes_match_header_prototypes(built_lib):
+    """Every binding the Python host side declares has as many `argtypes` as the C prototype has parameters."""
+    from musev_b200 import _capi, controlnet, referencenet, unet, vae
+    lib = _capi.lib()
+    for mod in (unet, controlnet, referencenet, vae):
+        mod._lib()
+    protos = _prototypes()
+    bound = 0
+    for name, nparams in protos.items():
+        fn = getattr(lib, name)
+        if fn.argtypes is None:
+            continue                      # C-only entry (not called from the Python mirror)
+        bound += 1
+        assert len(fn.argtypes) == nparams, (name, len(fn.argtypes), nparams)
+    assert bound >= 25, bound
